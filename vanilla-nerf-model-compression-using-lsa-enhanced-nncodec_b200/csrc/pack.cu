@@ -1,0 +1,135 @@
+// Packing of one NeRF network into the format the fused MLP kernels stream (net_layout.h):
+// weight levels -> fp16 (forward, W) and bf16 (backward, W^T) K-major SWIZZLE_64B stage images,
+// plus the per-channel epilogue constants {delta * lsa_scale, bias}.
+//
+// The reference keeps, per Linear layer, a float32 `weight` that holds dequantised values
+// level*delta (nnc_core/approximator/baseline.py:73-101 feeding framework/pytorch_model/__init__.py:
+// 1093-1111) and a `weight_scaling` [out,1] (transforms.py:94).  Here the integer levels themselves are
+// the tensor-core operands (exact in fp16 up to |level| <= 2048) and delta*scale is applied in the
+// epilogue, so dequantisation never materialises a float weight tensor.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "net_layout.h"
+#include "ptx_sm100.cuh"
+
+namespace nerfq {
+
+struct PackParams {
+    const void* w[kNumLayers];   // per layer [out, in] row-major; int32 levels or float32 values
+    float delta[kNumLayers];
+    uint8_t* packed;
+    int src_is_int32;
+};
+
+__device__ __constant__ MmaStep kFwdTab[kFwdSteps] = NERFQ_FWD_STEP_TABLE;
+__device__ __constant__ MmaStep kBwdTab[kBwdSteps] = NERFQ_BWD_STEP_TABLE;
+__device__ __constant__ int kInDev[kNumLayers] = {63, 256, 256, 256, 256, 319, 256, 256, 256, 256, 283, 128};
+__device__ __constant__ int kOutDev[kNumLayers] = {256, 256, 256, 256, 256, 256, 256, 256, 1, 256, 128, 3};
+__device__ __constant__ int kChDev[kNumLayers] = {0, 256, 512, 768, 1024, 1280, 1536, 1792, kChAlpha, kChFeature, kChViews, kChRgb};
+
+__device__ __forceinline__ float load_w(const PackParams& p, int layer, int idx) {
+    return p.src_is_int32 ? (float)reinterpret_cast<const int32_t*>(p.w[layer])[idx]
+                          : reinterpret_cast<const float*>(p.w[layer])[idx];
+}
+
+// grid = kFwdStages + kBwdStages blocks; block b packs one stage.
+__global__ void pack_images_kernel(const PackParams p) {
+    const bool bwd = blockIdx.x >= kFwdStages;
+    int sidx = bwd ? blockIdx.x - kFwdStages : blockIdx.x;
+    const MmaStep* tab = bwd ? kBwdTab : kFwdTab;
+    const int nsteps = bwd ? kBwdSteps : kFwdSteps;
+    uint32_t off = 0;
+    int s = 0;
+    for (; s < nsteps; ++s) {
+        if (sidx < tab[s].stages) break;
+        sidx -= tab[s].stages;
+        off += tab[s].stages * tab[s].n * kStageRowBytes;
+    }
+    const MmaStep st = tab[s];
+    off += sidx * st.n * kStageRowBytes;
+    uint8_t* dst = p.packed + (bwd ? kOffBwdImage : kOffFwdImage) + off;
+    const int in = kInDev[st.layer];
+    for (int item = threadIdx.x; item < st.n * 4; item += blockDim.x) {
+        const int n = item >> 2, chunk = item & 3;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int kk = sidx * kStageK + chunk * 8 + e;     // position along K within the step
+            float x = 0.0f;
+            if (kk < st.ncols) {
+                // forward: B[n][kk] = W[n][col0 + kk];   backward: B[n][kk] = W[o = kk][col0 + n]
+                x = bwd ? load_w(p, st.layer, kk * in + st.col0 + n) : load_w(p, st.layer, n * in + st.col0 + kk);
+            }
+            v[e] = x;
+        }
+        uint4 q;
+        if (bwd) {
+            q.x = pack_bf162(v[0], v[1]); q.y = pack_bf162(v[2], v[3]); q.z = pack_bf162(v[4], v[5]); q.w = pack_bf162(v[6], v[7]);
+        } else {
+            q.x = pack_half2(v[0], v[1]); q.y = pack_half2(v[2], v[3]); q.z = pack_half2(v[4], v[5]); q.w = pack_half2(v[6], v[7]);
+        }
+        *reinterpret_cast<uint4*>(dst + sw64_offset(n, chunk)) = q;
+    }
+}
+
+// per-channel delta, and the alpha / rgb head weights as float levels
+__global__ void pack_small_kernel(const PackParams p) {
+    float* delta = reinterpret_cast<float*>(p.packed + kOffDelta);
+    float* wa = reinterpret_cast<float*>(p.packed + kOffWAlpha);
+    float* wr = reinterpret_cast<float*>(p.packed + kOffWRgb);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kNumChannels + 256 + 384; i += gridDim.x * blockDim.x) {
+        if (i < kNumChannels) {
+            int layer = 0;
+            for (int l = 0; l < kNumLayers; ++l)
+                if (i >= kChDev[l] && i < kChDev[l] + kOutDev[l]) layer = l;
+            delta[i] = p.delta[layer];
+        } else if (i < kNumChannels + 256) {
+            wa[i - kNumChannels] = load_w(p, 8, i - kNumChannels);
+        } else {
+            wr[i - kNumChannels - 256] = load_w(p, 11, i - kNumChannels - 256);
+        }
+    }
+}
+
+// sb[ch] = {delta[ch] * scale[ch], bias[ch]};  scale == nullptr means 1 (no LSA).
+__global__ void set_scale_bias_kernel(uint8_t* packed, const float* __restrict__ scale, const float* __restrict__ bias) {
+    const float* delta = reinterpret_cast<const float*>(packed + kOffDelta);
+    float2* sb = reinterpret_cast<float2*>(packed + kOffSB);
+    float* sc = reinterpret_cast<float*>(packed + kOffScale);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kNumChannels; i += gridDim.x * blockDim.x) {
+        const float s = scale ? scale[i] : 1.0f;
+        sc[i] = s;
+        sb[i] = make_float2(delta[i] * s, bias[i]);
+    }
+}
+
+}  // namespace nerfq
+
+extern "C" unsigned long long nerfq_packed_net_bytes(void) { return nerfq::kPackedBytes; }
+extern "C" int nerfq_num_channels(void) { return nerfq::kNumChannels; }
+
+extern "C" int nerfq_pack_net(void* packed, const void* const* weights12, const float* delta12, int src_is_int32,
+                              cudaStream_t stream) {
+    using namespace nerfq;
+    if (!packed || !weights12 || !delta12) return -1;
+    PackParams p;
+    for (int l = 0; l < kNumLayers; ++l) {
+        if (!weights12[l]) return -1;
+        p.w[l] = weights12[l];
+        p.delta[l] = delta12[l];
+    }
+    p.packed = reinterpret_cast<uint8_t*>(packed);
+    p.src_is_int32 = src_is_int32;
+    pack_images_kernel<<<kFwdStages + kBwdStages, 256, 0, stream>>>(p);
+    pack_small_kernel<<<8, 256, 0, stream>>>(p);
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+extern "C" int nerfq_set_scale_bias(void* packed, const float* scale, const float* bias, cudaStream_t stream) {
+    using namespace nerfq;
+    if (!packed || !bias) return -1;
+    set_scale_bias_kernel<<<5, 512, 0, stream>>>(reinterpret_cast<uint8_t*>(packed), scale, bias);
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
