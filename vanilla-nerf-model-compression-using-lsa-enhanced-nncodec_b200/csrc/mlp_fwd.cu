@@ -316,9 +316,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const FwdParam
 extern "C" int nerfq_mlp_forward(const void* packed, const float* rays, const float* z, long long n_rays,
                                  int samples_per_ray, float* raw, void* save, int pingpong, int max_ctas, cudaStream_t stream) {
     using namespace nerfq;
+    if (n_rays == 0) return 0;
     if (!packed || !rays || !z || !raw || n_rays < 0 || samples_per_ray <= 0) return -1;
     const long long n_points = n_rays * samples_per_ray;
-    if (n_points == 0) return 0;
     const long long n_tiles = (n_points + kTileM - 1) / kTileM;
     const int n_pairs = (int)((n_tiles + 1) / 2);
     int dev = 0, sms = 0;

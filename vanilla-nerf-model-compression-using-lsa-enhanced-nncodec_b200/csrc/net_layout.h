@@ -97,7 +97,7 @@ constexpr int kFwdImageBytes = image_bytes(kFwd, kFwdSteps);
 constexpr int kBwdImageBytes = image_bytes(kBwd, kBwdSteps);
 
 // ---- packed network buffer -------------------------------------------------------------------
-// [ fwd image (fp16) | bwd image (bf16) | sb: float2{eff_scale, bias}[2436] | delta[2436] |
+// [ fwd image (fp16) | bwd image (fp16) | sb: float2{eff_scale, bias}[2436] | delta[2436] |
 //   w_alpha float[256] (levels) | w_rgb float[3*128] (levels) ]
 constexpr size_t kOffFwdImage = 0;
 constexpr size_t kOffBwdImage = kOffFwdImage + kFwdImageBytes;

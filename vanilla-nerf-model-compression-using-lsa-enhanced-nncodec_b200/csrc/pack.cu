@@ -1,5 +1,5 @@
 // Packing of one NeRF network into the format the fused MLP kernels stream (net_layout.h):
-// weight levels -> fp16 (forward, W) and bf16 (backward, W^T) K-major SWIZZLE_64B stage images,
+// weight levels -> fp16 K-major SWIZZLE_64B stage images of W (forward) and W^T (backward),
 // plus the per-channel epilogue constants {delta * lsa_scale, bias}.
 //
 // The reference keeps, per Linear layer, a float32 `weight` that holds dequantised values
@@ -65,11 +65,7 @@ __global__ void pack_images_kernel(const PackParams p) {
             v[e] = x;
         }
         uint4 q;
-        if (bwd) {
-            q.x = pack_bf162(v[0], v[1]); q.y = pack_bf162(v[2], v[3]); q.z = pack_bf162(v[4], v[5]); q.w = pack_bf162(v[6], v[7]);
-        } else {
-            q.x = pack_half2(v[0], v[1]); q.y = pack_half2(v[2], v[3]); q.z = pack_half2(v[4], v[5]); q.w = pack_half2(v[6], v[7]);
-        }
+        q.x = pack_half2(v[0], v[1]); q.y = pack_half2(v[2], v[3]); q.z = pack_half2(v[4], v[5]); q.w = pack_half2(v[6], v[7]);
         *reinterpret_cast<uint4*>(dst + sw64_offset(n, chunk)) = q;
     }
 }

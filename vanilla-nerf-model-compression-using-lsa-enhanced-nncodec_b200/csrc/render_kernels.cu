@@ -1,0 +1,516 @@
+// HBM-bound kernels of the ray-rendering path (one warp per ray, coalesced segment-per-lane access):
+//   nerfq_coarse_depths   stratified depths                       run_nerf.py:379-403
+//   nerfq_composite_fwd   raw2outputs                             run_nerf.py:285-345
+//   nerfq_composite_bwd   its gradient w.r.t. raw (autograd equivalent)
+//   nerfq_sample_fine     sample_pdf + concat + sort + z_std      run_nerf_helpers.py:119-163, run_nerf.py:423-429,451
+//   nerfq_camera_rays / nerfq_pack_rays   get_rays, viewdirs, ndc_rays, ray packing   run_nerf_helpers.py:71-115, run_nerf.py:108-142
+//   nerfq_mse_grad        img2mse (x2) and its gradient           run_nerf_helpers.py:12, run_nerf.py:741-751
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace nerfq {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kMaxPerLane = 8;      // samples per lane: supports up to 256 samples per ray
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+// exclusive product / sum scans across lanes (lane 0 gets the identity)
+__device__ __forceinline__ float warp_excl_prod(float v, int lane) {
+    float incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl *= t;
+    }
+    float ex = __shfl_up_sync(kFull, incl, 1);
+    return lane == 0 ? 1.0f : ex;
+}
+__device__ __forceinline__ float warp_excl_sum(float v, int lane) {
+    float incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+    }
+    float ex = __shfl_up_sync(kFull, incl, 1);
+    return lane == 0 ? 0.0f : ex;
+}
+// suffix (reverse) exclusive sum across lanes: lane i gets sum over lanes > i
+__device__ __forceinline__ float warp_excl_suffix_sum(float v, int lane) {
+    float incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_down_sync(kFull, incl, o);
+        if (lane + o < 32) incl += t;
+    }
+    float ex = __shfl_down_sync(kFull, incl, 1);
+    return lane == 31 ? 0.0f : ex;
+}
+
+// torch.linspace(0, 1, n)[i] as ATen's CUDA kernel computes it (symmetric halves, fused multiply-add);
+// ATen's vectorised CPU kernel differs from this in the last bit of some entries.
+__device__ __forceinline__ float linspace01(int i, int n) {
+    const float step = 1.0f / (float)(n - 1);
+    return i < n / 2 ? fmaf(step, (float)i, 0.0f) : fmaf(-step, (float)(n - 1 - i), 1.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// coarse depths
+// ---------------------------------------------------------------------------------------------
+__global__ void coarse_depths_kernel(const float* __restrict__ rays, const float* __restrict__ t_rand, long long n_rays, int S,
+                                     int lindisp, float* __restrict__ z_out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_rays * S) return;
+    const long long ray = idx / S;
+    const int i = (int)(idx - ray * S);
+    const float near = rays[ray * 11 + 6], far = rays[ray * 11 + 7];
+    auto base = [&](int k) {
+        const float t = linspace01(k, S);
+        const float omt = __fsub_rn(1.0f, t);
+        if (lindisp) return __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(__fdiv_rn(1.0f, near), omt), __fmul_rn(__fdiv_rn(1.0f, far), t)));
+        return __fadd_rn(__fmul_rn(near, omt), __fmul_rn(far, t));
+    };
+    float z = base(i);
+    if (t_rand) {
+        const float lower = i == 0 ? z : __fmul_rn(0.5f, __fadd_rn(z, base(i - 1)));
+        const float upper = i == S - 1 ? z : __fmul_rn(0.5f, __fadd_rn(base(i + 1), z));
+        z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t_rand[idx]));
+    }
+    z_out[idx] = z;
+}
+
+// ---------------------------------------------------------------------------------------------
+// compositing
+// ---------------------------------------------------------------------------------------------
+struct RaySeg {
+    float alpha[kMaxPerLane], dist[kMaxPerLane], sig[kMaxPerLane], zz[kMaxPerLane];
+    float c[kMaxPerLane][3];
+};
+
+// Loads this lane's contiguous segment [lane*per, lane*per+per) of one ray and evaluates alpha / colour.
+__device__ __forceinline__ void load_segment(RaySeg& s, const float* __restrict__ raw, const float* __restrict__ z,
+                                             const float* __restrict__ noise, float dnorm, int S, int per, int lane) {
+    const int i0 = lane * per;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+        const int i = i0 + k;
+        if (k < per && i < S) {
+            const float4 r = *reinterpret_cast<const float4*>(raw + 4 * i);
+            const float zi = z[i];
+            const float gap = (i + 1 < S) ? __fsub_rn(z[i + 1], zi) : 1e10f;
+            const float d = __fmul_rn(gap, dnorm);
+            float sg = r.w;
+            if (noise) sg = __fadd_rn(sg, noise[i]);
+            s.sig[k] = sg;
+            s.dist[k] = d;
+            s.zz[k] = zi;
+            s.alpha[k] = __fsub_rn(1.0f, expf(-__fmul_rn(fmaxf(sg, 0.0f), d)));
+            s.c[k][0] = 1.0f / (1.0f + expf(-r.x));
+            s.c[k][1] = 1.0f / (1.0f + expf(-r.y));
+            s.c[k][2] = 1.0f / (1.0f + expf(-r.z));
+        } else {
+            s.sig[k] = 0.f; s.dist[k] = 0.f; s.zz[k] = 0.f; s.alpha[k] = 0.f;
+            s.c[k][0] = s.c[k][1] = s.c[k][2] = 0.f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32 * kWarpsPerBlock) composite_fwd_kernel(
+    const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays, const float* __restrict__ noise,
+    int white_bkgd, long long n_rays, int S, float* __restrict__ rgb, float* __restrict__ disp, float* __restrict__ acc,
+    float* __restrict__ depth, float* __restrict__ weights) {
+    const int lane = threadIdx.x & 31;
+    const long long ray = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (ray >= n_rays) return;
+    const int per = (S + 31) / 32;
+    const float* r = rays + ray * 11;
+    const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(r[3], r[3]), __fmul_rn(r[4], r[4])), __fmul_rn(r[5], r[5])));
+    RaySeg s;
+    load_segment(s, raw + ray * S * 4, z + ray * S, noise ? noise + ray * S : nullptr, dnorm, S, per, lane);
+    float prod = 1.0f;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k)
+        if (k < per) prod *= __fadd_rn(__fsub_rn(1.0f, s.alpha[k]), 1e-10f);
+    float T = warp_excl_prod(prod, lane);
+    float a_rgb[3] = {0.f, 0.f, 0.f}, a_depth = 0.f, a_acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+        const int i = lane * per + k;
+        if (k < per && i < S) {
+            const float w = __fmul_rn(s.alpha[k], T);
+            T *= __fadd_rn(__fsub_rn(1.0f, s.alpha[k]), 1e-10f);
+            if (weights) weights[ray * S + i] = w;
+            a_rgb[0] = fmaf(w, s.c[k][0], a_rgb[0]);
+            a_rgb[1] = fmaf(w, s.c[k][1], a_rgb[1]);
+            a_rgb[2] = fmaf(w, s.c[k][2], a_rgb[2]);
+            a_depth = fmaf(w, s.zz[k], a_depth);
+            a_acc += w;
+        }
+    }
+    a_rgb[0] = warp_sum(a_rgb[0]); a_rgb[1] = warp_sum(a_rgb[1]); a_rgb[2] = warp_sum(a_rgb[2]);
+    a_depth = warp_sum(a_depth); a_acc = warp_sum(a_acc);
+    if (lane == 0) {
+        if (white_bkgd) {
+            const float bg = __fsub_rn(1.0f, a_acc);
+            a_rgb[0] += bg; a_rgb[1] += bg; a_rgb[2] += bg;
+        }
+        rgb[ray * 3 + 0] = a_rgb[0]; rgb[ray * 3 + 1] = a_rgb[1]; rgb[ray * 3 + 2] = a_rgb[2];
+        const float q = __fdiv_rn(a_depth, a_acc);                  // 0/0 -> NaN, propagated like torch.max does
+        const float m = (q != q) ? q : fmaxf(1e-10f, q);
+        disp[ray] = __fdiv_rn(1.0f, m);
+        acc[ray] = a_acc;
+        if (depth) depth[ray] = a_depth;
+    }
+}
+
+// d_raw from d_rgb (the only output the LSA objective uses, run_nerf.py:741-751).
+__global__ void __launch_bounds__(32 * kWarpsPerBlock) composite_bwd_kernel(
+    const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays, const float* __restrict__ noise,
+    int white_bkgd, const float* __restrict__ d_rgb, long long n_rays, int S, float* __restrict__ d_raw) {
+    const int lane = threadIdx.x & 31;
+    const long long ray = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (ray >= n_rays) return;
+    const int per = (S + 31) / 32;
+    const float* r = rays + ray * 11;
+    const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(r[3], r[3]), __fmul_rn(r[4], r[4])), __fmul_rn(r[5], r[5])));
+    RaySeg s;
+    load_segment(s, raw + ray * S * 4, z + ray * S, noise ? noise + ray * S : nullptr, dnorm, S, per, lane);
+    const float g0 = d_rgb[ray * 3 + 0], g1 = d_rgb[ray * 3 + 1], g2 = d_rgb[ray * 3 + 2];
+    const float gbg = white_bkgd ? (g0 + g1 + g2) : 0.0f;
+    float prod = 1.0f;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k)
+        if (k < per) prod *= __fadd_rn(__fsub_rn(1.0f, s.alpha[k]), 1e-10f);
+    float T = warp_excl_prod(prod, lane);
+    float Tk[kMaxPerLane], wk[kMaxPerLane], dwk[kMaxPerLane];
+    float seg = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+        Tk[k] = T;
+        wk[k] = s.alpha[k] * T;
+        dwk[k] = g0 * s.c[k][0] + g1 * s.c[k][1] + g2 * s.c[k][2] - gbg;     // dL/dw_i
+        if (k < per) {
+            T *= __fadd_rn(__fsub_rn(1.0f, s.alpha[k]), 1e-10f);
+            seg += dwk[k] * wk[k];
+        }
+    }
+    float suffix = warp_excl_suffix_sum(seg, lane);      // sum over later lanes of dw*w
+#pragma unroll
+    for (int k = kMaxPerLane - 1; k >= 0; --k) {
+        const int i = lane * per + k;
+        if (k < per && i < S) {
+            const float a = __fadd_rn(__fsub_rn(1.0f, s.alpha[k]), 1e-10f);
+            const float dalpha = dwk[k] * Tk[k] - suffix / a;
+            const float dsig = (s.sig[k] > 0.0f) ? dalpha * s.dist[k] * (1.0f - s.alpha[k]) : 0.0f;
+            float4 o;
+            o.x = g0 * wk[k] * s.c[k][0] * (1.0f - s.c[k][0]);
+            o.y = g1 * wk[k] * s.c[k][1] * (1.0f - s.c[k][1]);
+            o.z = g2 * wk[k] * s.c[k][2] * (1.0f - s.c[k][2]);
+            o.w = dsig;
+            *reinterpret_cast<float4*>(d_raw + (ray * S + i) * 4) = o;
+            suffix += dwk[k] * wk[k];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// importance sampling + merge
+// ---------------------------------------------------------------------------------------------
+// One warp per ray.  Shared memory per warp: cdf[S-1], bins[S-1], sort buffer[P] with P = pow2 >= S+Ni.
+__global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_fine_kernel(
+    const float* __restrict__ z_coarse, const float* __restrict__ bins_in, const float* __restrict__ weights,
+    const float* __restrict__ u_in, long long n_rays, int S, int Ni, int P, float* __restrict__ z_out, float* __restrict__ z_std,
+    float* __restrict__ z_samples_out) {
+    extern __shared__ float sm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long ray = (long long)blockIdx.x * kWarpsPerBlock + wib;
+    const int nb = S - 1;                     // bins (midpoints) == cdf entries
+    float* cdf = sm + (size_t)wib * (2 * nb + P);
+    float* bins = cdf + nb;
+    float* srt = bins + nb;
+    if (ray >= n_rays) return;
+    const float* zc = z_coarse ? z_coarse + ray * S : nullptr;
+    const float* w = weights + ray * S;
+    // pdf over the S-2 interior weights, cdf = [0, cumsum]
+    const int nw = S - 2;
+    const int per = (nw + 31) / 32;
+    float loc[kMaxPerLane];
+    float lsum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+        const int j = lane * per + k;
+        loc[k] = (k < per && j < nw) ? __fadd_rn(w[j + 1], 1e-5f) : 0.0f;
+        lsum += loc[k];
+    }
+    const float total = warp_sum(lsum);
+    // cdf = [0, cumsum(pdf)].  ATen's CPU cumsum accumulates float rows in double and rounds each prefix
+    // once; scanning in double reproduces those prefixes (the denom < 1e-5 branch below is decided by the
+    // last bit of neighbouring cdf entries, so the rounding of the scan matters).
+    double lp = 0.0;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+        loc[k] = __fdiv_rn(loc[k], total);
+        lp += (double)loc[k];
+    }
+    double incl = lp;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+    }
+    double run = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) run = 0.0;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+        const int j = lane * per + k;
+        if (k < per && j < nw) {
+            run += (double)loc[k];
+            cdf[j + 1] = (float)run;
+        }
+    }
+    if (lane == 0) cdf[0] = 0.0f;
+    if (bins_in) {
+        for (int j = lane; j < nb; j += 32) bins[j] = bins_in[ray * nb + j];
+    } else {
+        for (int j = lane; j < nb; j += 32) bins[j] = __fmul_rn(0.5f, __fadd_rn(zc[j + 1], zc[j]));
+    }
+    if (zc) for (int j = lane; j < S; j += 32) srt[j] = zc[j];
+    for (int j = S + Ni + lane; j < P; j += 32) srt[j] = CUDART_INF_F;
+    __syncwarp();
+    // inverse CDF
+    float m1 = 0.0f;
+    for (int k = lane; k < Ni; k += 32) {
+        const float u = u_in ? u_in[ray * Ni + k] : linspace01(k, Ni);
+        int lo = 0, hi = nb;                              // first index with cdf[idx] > u  (searchsorted right=True)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+        }
+        const int below = max(lo - 1, 0), above = min(lo, nb - 1);
+        const float c0 = cdf[below], c1 = cdf[above];
+        float den = __fsub_rn(c1, c0);
+        if (den < 1e-5f) den = 1.0f;
+        const float t = __fdiv_rn(__fsub_rn(u, c0), den);
+        const float b0 = bins[below], b1 = bins[above];
+        const float zs = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+        srt[S + k] = zs;
+        if (z_samples_out) z_samples_out[ray * Ni + k] = zs;
+        m1 += zs;
+    }
+    // z_std = std(z_samples, unbiased=False)
+    const float mean = warp_sum(m1) / (float)Ni;
+    __syncwarp();
+    float m2 = 0.0f;
+    for (int k = lane; k < Ni; k += 32) {
+        const float d = srt[S + k] - mean;
+        m2 = fmaf(d, d, m2);
+    }
+    m2 = warp_sum(m2);
+    if (lane == 0 && z_std) z_std[ray] = sqrtf(m2 / (float)Ni);
+    if (!z_out) return;
+    // bitonic sort of P values in shared memory
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncwarp();
+            for (int t = lane; t < P / 2; t += 32) {
+                const int i = 2 * t - (t & (stride - 1));
+                const int j = i + stride;
+                const bool up = (i & size) == 0;
+                const float a = srt[i], b = srt[j];
+                if ((a > b) == up) { srt[i] = b; srt[j] = a; }
+            }
+        }
+    }
+    __syncwarp();
+    for (int j = lane; j < S + Ni; j += 32) z_out[ray * (S + Ni) + j] = srt[j];
+}
+
+// ---------------------------------------------------------------------------------------------
+// ray generation and packing: rows [o(3), d(3), near, far, viewdir(3)]
+// ---------------------------------------------------------------------------------------------
+struct CamParams {
+    float fx, fy, cx, cy;
+    float c2w[12];           // 3x4 row-major
+    int H, W;
+    int ndc;
+    float near, far;
+    float ndc_ax, ndc_ay;    // -1/(W/(2 focal)), -1/(H/(2 focal)) evaluated in double on the host like the reference's Python scalars
+};
+
+__device__ __forceinline__ void finish_ray(float o[3], float d[3], const CamParams& cp, float* __restrict__ out) {
+    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+    const float v0 = __fdiv_rn(d[0], nrm), v1 = __fdiv_rn(d[1], nrm), v2 = __fdiv_rn(d[2], nrm);
+    if (cp.ndc) {   // run_nerf_helpers.py:98-115 with near = 1
+        const float t = __fdiv_rn(-__fadd_rn(1.0f, o[2]), d[2]);
+        o[0] = __fadd_rn(o[0], __fmul_rn(t, d[0]));
+        o[1] = __fadd_rn(o[1], __fmul_rn(t, d[1]));
+        o[2] = __fadd_rn(o[2], __fmul_rn(t, d[2]));
+        const float ax = cp.ndc_ax, ay = cp.ndc_ay;
+        const float ox = __fdiv_rn(o[0], o[2]), oy = __fdiv_rn(o[1], o[2]);
+        const float n0 = __fdiv_rn(__fmul_rn(ax, o[0]), o[2]), n1 = __fdiv_rn(__fmul_rn(ay, o[1]), o[2]);
+        const float n2 = __fadd_rn(1.0f, __fdiv_rn(2.0f, o[2]));
+        const float e0 = __fmul_rn(ax, __fsub_rn(__fdiv_rn(d[0], d[2]), ox));
+        const float e1 = __fmul_rn(ay, __fsub_rn(__fdiv_rn(d[1], d[2]), oy));
+        const float e2 = __fdiv_rn(-2.0f, o[2]);
+        o[0] = n0; o[1] = n1; o[2] = n2; d[0] = e0; d[1] = e1; d[2] = e2;
+    }
+    out[0] = o[0]; out[1] = o[1]; out[2] = o[2];
+    out[3] = d[0]; out[4] = d[1]; out[5] = d[2];
+    out[6] = cp.near; out[7] = cp.far;
+    out[8] = v0; out[9] = v1; out[10] = v2;
+}
+
+// rays for pixels [first, first+count) of an H x W image, row-major (run_nerf_helpers.py:71-85)
+__global__ void camera_rays_kernel(const CamParams cp, long long first, long long count, float* __restrict__ out) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const long long pix = first + k;
+    const int j = (int)(pix / cp.W), i = (int)(pix - (long long)j * cp.W);
+    const float dx = __fdiv_rn(__fsub_rn((float)i, cp.cx), cp.fx);
+    const float dy = -__fdiv_rn(__fsub_rn((float)j, cp.cy), cp.fy);
+    const float dz = -1.0f;
+    float o[3], d[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        d[r] = __fadd_rn(__fadd_rn(__fmul_rn(dx, cp.c2w[4 * r + 0]), __fmul_rn(dy, cp.c2w[4 * r + 1])), __fmul_rn(dz, cp.c2w[4 * r + 2]));
+        o[r] = cp.c2w[4 * r + 3];
+    }
+    finish_ray(o, d, cp, out + k * 11);
+}
+
+__global__ void pack_rays_kernel(const CamParams cp, const float* __restrict__ rays_o, const float* __restrict__ rays_d, long long n,
+                                 float* __restrict__ out) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float o[3] = {rays_o[3 * k], rays_o[3 * k + 1], rays_o[3 * k + 2]};
+    float d[3] = {rays_d[3 * k], rays_d[3 * k + 1], rays_d[3 * k + 2]};
+    finish_ray(o, d, cp, out + k * 11);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LSA objective: loss = mean((rgb-t)^2) + mean((rgb0-t)^2); gradients 2(rgb-t)/(3N)
+// ---------------------------------------------------------------------------------------------
+__global__ void mse_grad_kernel(const float* __restrict__ rgb, const float* __restrict__ rgb0, const float* __restrict__ target,
+                                long long n3, float* __restrict__ d_rgb, float* __restrict__ d_rgb0, float* __restrict__ loss2) {
+    float s0 = 0.f, s1 = 0.f;
+    const float k = 2.0f / (float)n3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long long)gridDim.x * blockDim.x) {
+        const float t = target[i];
+        const float a = rgb[i] - t;
+        s0 = fmaf(a, a, s0);
+        d_rgb[i] = k * a;
+        if (rgb0) {
+            const float b = rgb0[i] - t;
+            s1 = fmaf(b, b, s1);
+            d_rgb0[i] = k * b;
+        }
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(loss2 + 0, s0 / (float)n3);
+        atomicAdd(loss2 + 1, s1 / (float)n3);
+    }
+}
+
+}  // namespace nerfq
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+using namespace nerfq;
+static inline int launch_ok() { return cudaGetLastError() == cudaSuccess ? 0 : -3; }
+
+extern "C" int nerfq_coarse_depths(const float* rays, const float* t_rand, long long n_rays, int S, int lindisp, float* z_out,
+                                   cudaStream_t stream) {
+    if (n_rays == 0) return 0;
+    if (!rays || !z_out || S < 2 || n_rays < 0) return -1;
+    const long long total = n_rays * S;
+    coarse_depths_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(rays, t_rand, n_rays, S, lindisp, z_out);
+    return launch_ok();
+}
+
+extern "C" int nerfq_composite_fwd(const float* raw, const float* z, const float* rays, const float* noise, int white_bkgd,
+                                   long long n_rays, int S, float* rgb, float* disp, float* acc, float* depth, float* weights,
+                                   cudaStream_t stream) {
+    if (n_rays == 0) return 0;
+    if (!raw || !z || !rays || !rgb || !disp || !acc || S < 1 || S > 32 * kMaxPerLane || n_rays < 0) return -1;
+    composite_fwd_kernel<<<(unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock), 32 * kWarpsPerBlock, 0, stream>>>(
+        raw, z, rays, noise, white_bkgd, n_rays, S, rgb, disp, acc, depth, weights);
+    return launch_ok();
+}
+
+extern "C" int nerfq_composite_bwd(const float* raw, const float* z, const float* rays, const float* noise, int white_bkgd,
+                                   const float* d_rgb, long long n_rays, int S, float* d_raw, cudaStream_t stream) {
+    if (n_rays == 0) return 0;
+    if (!raw || !z || !rays || !d_rgb || !d_raw || S < 1 || S > 32 * kMaxPerLane || n_rays < 0) return -1;
+    composite_bwd_kernel<<<(unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock), 32 * kWarpsPerBlock, 0, stream>>>(
+        raw, z, rays, noise, white_bkgd, d_rgb, n_rays, S, d_raw);
+    return launch_ok();
+}
+
+// Either z_coarse [N,S] (bins = its midpoints; z_out receives the sorted union) or bins [N,S-1] (sample_pdf
+// proper; z_out must be null).  weights is [N,S]; only the S-2 interior entries are read.
+extern "C" int nerfq_sample_fine(const float* z_coarse, const float* bins, const float* weights, const float* u, long long n_rays,
+                                 int S, int Ni, float* z_out, float* z_std, float* z_samples, cudaStream_t stream) {
+    if (n_rays == 0) return 0;
+    if ((!z_coarse && !bins) || !weights || (z_out && !z_coarse) || (!z_out && !z_samples) || S < 3 || S - 2 > 32 * kMaxPerLane ||
+        Ni < 1 || n_rays < 0)
+        return -1;
+    int P = 2;
+    while (P < S + Ni) P <<= 1;
+    const size_t smem = (size_t)kWarpsPerBlock * (2 * (S - 1) + P) * sizeof(float);
+    if (smem > 200 * 1024) return -1;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(sample_fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sample_fine_kernel<<<(unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock), 32 * kWarpsPerBlock, smem, stream>>>(
+        z_coarse, bins, weights, u, n_rays, S, Ni, P, z_out, z_std, z_samples);
+    return launch_ok();
+}
+
+static CamParams make_cam(int H, int W, const float* K4, const float* c2w12, int ndc, float near, float far, float ndc_focal) {
+    CamParams cp{};
+    if (K4) { cp.fx = K4[0]; cp.fy = K4[1]; cp.cx = K4[2]; cp.cy = K4[3]; }
+    if (c2w12) for (int i = 0; i < 12; ++i) cp.c2w[i] = c2w12[i];
+    cp.H = H; cp.W = W; cp.ndc = ndc; cp.near = near; cp.far = far;
+    if (ndc) {
+        cp.ndc_ax = (float)(-1.0 / ((double)W / (2.0 * (double)ndc_focal)));
+        cp.ndc_ay = (float)(-1.0 / ((double)H / (2.0 * (double)ndc_focal)));
+    }
+    return cp;
+}
+
+// K4 = {fx, fy, cx, cy} and c2w12 (3x4 row-major) are HOST pointers (tiny, passed by value to the kernel).
+extern "C" int nerfq_camera_rays(int H, int W, const float* K4, const float* c2w12, int ndc, float near, float far,
+                                 long long first_pixel, long long count, float* rays_out, cudaStream_t stream) {
+    if (count == 0) return 0;
+    if (!K4 || !c2w12 || !rays_out || H <= 0 || W <= 0 || first_pixel < 0 || count < 0 || first_pixel + count > (long long)H * W) return -1;
+    const CamParams cp = make_cam(H, W, K4, c2w12, ndc, near, far, K4[0]);
+    camera_rays_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(cp, first_pixel, count, rays_out);
+    return launch_ok();
+}
+
+extern "C" int nerfq_pack_rays(const float* rays_o, const float* rays_d, long long n, int ndc, int H, int W, float focal, float near,
+                               float far, float* rays_out, cudaStream_t stream) {
+    if (n == 0) return 0;
+    if (!rays_o || !rays_d || !rays_out || n < 0) return -1;
+    const CamParams cp = make_cam(H, W, nullptr, nullptr, ndc, near, far, focal);
+    pack_rays_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(cp, rays_o, rays_d, n, rays_out);
+    return launch_ok();
+}
+
+// loss2 must be zeroed by the caller; receives {mse(rgb,t), mse(rgb0,t)}.
+extern "C" int nerfq_mse_grad(const float* rgb, const float* rgb0, const float* target, long long n_rays, float* d_rgb,
+                              float* d_rgb0, float* loss2, cudaStream_t stream) {
+    if (n_rays == 0) return 0;
+    if (!rgb || !target || !d_rgb || !loss2 || (rgb0 && !d_rgb0) || n_rays < 0) return -1;
+    const long long n3 = n_rays * 3;
+    long long blocks = (n3 + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    mse_grad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rgb, rgb0, target, n3, d_rgb, d_rgb0, loss2);
+    return launch_ok();
+}
