@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the NeRF ray-rendering hot path (BASELINE.json metric: rays/sec through render_rays with
+64+128 samples per ray; LSA steps/sec).
+
+    python bench.py --gpus N --steps K --warmup W             # this implementation (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU (oracle port)
+
+One "step" is BASELINE configs[1]: an LSA fine-tuning step at qp=-20 on a 4096-ray batch per GPU
+(quantise -> on-the-fly LSA-scaled dequantisation -> render 64+128 -> backward into the LSA scales -> Adam),
+synthetic rays and a random-init vanilla NeRF.  Multi-GPU runs are data parallel (weak scaling: 4096 rays per
+GPU, one 19.5 KB NCCL all-reduce of the scale gradients per step).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RAYS_PER_GPU = 4096
+N_SAMPLES, N_IMPORTANCE = 64, 128
+QP, QP_DENSITY, NONWEIGHT_QP = -20, 2, -75
+FLOP_PER_POINT_FWD = 2 * 593408
+FLOP_PER_POINT_BWD = 2 * 557696
+METRIC = "rays/sec render_rays (64+128 samples/ray); LSA steps/sec"
+
+
+def synth_batch(n, seed, device="cpu"):
+    g = torch.Generator().manual_seed(seed)
+    o = 0.1 * torch.randn(n, 3, generator=g) + torch.tensor([0.0, 0.0, 4.0])
+    d = torch.randn(n, 3, generator=g)
+    d = -d / torch.norm(d, dim=-1, keepdim=True)
+    target = torch.rand(n, 3, generator=torch.Generator().manual_seed(seed + 1))
+    return o.to(device), d.to(device), target.to(device)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"tensor": float(p["bf16_tflops_sustained"]), "tensor_burst": float(p["bf16_tflops"]), "hbm": float(p["hbm_gbs"]),
+                "source": "MEASURED_PEAKS.json"}
+    return {"tensor": 1400.0, "tensor_burst": 1590.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the reference algorithm on the host CPU (oracle port; /root/reference is torch-eager
+# Python that cannot travel to the GPU box and needs modules that are absent, so the oracle restatement,
+# pinned to the reference by tests/golden, is what is timed)
+# --------------------------------------------------------------------------------------------------
+def oracle_model(seed=0):
+    from oracle import quant_oracle as qo, render_oracle as ro  # noqa: F401  (bench's cpu legs may use oracle/)
+    import nerfq_b200  # noqa: F401
+    from nerfq_b200 import model as nmodel
+    torch.manual_seed(seed)
+    w = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params()
+    p = {}
+    for k, v in w.state_dict().items():
+        v = v.detach().clone()
+        if k.endswith(".weight"):
+            lv, _ = qo.quant_urq(v.numpy(), QP, QP_DENSITY)
+            v = torch.from_numpy(qo.dequant(lv, QP, QP_DENSITY))
+        elif k.endswith(".bias"):
+            lv, _ = qo.quant_urq(v.numpy(), NONWEIGHT_QP, QP_DENSITY)
+            v = torch.from_numpy(qo.dequant(lv, NONWEIGHT_QP, QP_DENSITY))
+        p[k] = v
+    return p
+
+
+def cpu_lsa_steps(p, n_rays, steps, warmup, seed=2):
+    """LSA steps of the oracle on `n_rays` rays with Adam on the scales; returns (sec per step, threads)."""
+    from oracle import render_oracle as ro
+    o, d, target = synth_batch(n_rays, seed)
+    batch, _ = ro.pack_rays(4, 4, None, rays=(o, d), ndc=False, near=2.0, far=6.0)
+    scales = {k: v.clone().requires_grad_(True) for k, v in p.items() if k.endswith("weight_scaling")}
+    frozen = {k: v for k, v in p.items() if not k.endswith("weight_scaling")}
+    opt = torch.optim.Adam(list(scales.values()), lr=1e-4)
+    g = torch.Generator().manual_seed(5)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        t_rand = torch.rand(n_rays, N_SAMPLES, generator=g)
+        u = torch.rand(n_rays, N_IMPORTANCE, generator=g)
+        out = ro.render_rays({**frozen, **scales}, batch, N_SAMPLES, N_IMPORTANCE, white_bkgd=True, t_rand=t_rand, u=u)
+        loss = ro.lsa_loss(out, target)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return float(np.mean(times)), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    sample = 512
+    p = oracle_model()
+    sec, threads = cpu_lsa_steps(p, sample, args.steps, max(args.warmup, 1))
+    rays_s = sample / sec
+    line = {"metric": METRIC, "value": rays_s, "unit": "rays/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3 * RAYS_PER_GPU / sample, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "lsa_steps_per_sec": rays_s / RAYS_PER_GPU,
+            "config": {"workload": "cfg2: LSA step qp=-20, 64+128 samples, random-init vanilla NeRF (CPU oracle port of the reference)",
+                       "rays_per_step_sample": sample, "rays_per_step_full": RAYS_PER_GPU},
+            "cpu_baseline": {"value": rays_s, "unit": "rays/s", "cores": threads, "kind": "port",
+                             "sample": f"{sample}-ray LSA steps (fwd+bwd+Adam), torch CPU fp32, mean of {args.steps}"},
+            "e2e": {"value": rays_s, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# this implementation
+# --------------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the nerfq kernels)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import nerfq_b200  # noqa: F401
+    from nerfq_b200 import codec, model as nmodel, ops, packed, render as R
+
+    torch.manual_seed(0)
+    wrapper = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params().to(dev)
+    master = {k: v.detach().clone() for k, v in wrapper.state_dict().items()}      # unquantised float weights
+    for name, prm in wrapper.named_parameters():
+        prm.requires_grad_(name.endswith("weight_scaling"))
+    params = [q for q in wrapper.parameters() if q.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-4)
+    train_kw, _ = R.create_nerf(wrapper, perturb=1.0, white_bkgd=True, dataset_type="blender")
+    R.DATA_PARALLEL["enabled"] = world > 1
+    R.TUNING["pingpong"] = not args.no_pingpong
+
+    o_h, d_h, t_h = synth_batch(RAYS_PER_GPU, 2 + 10 * rank)
+    rays_h = torch.stack([o_h, d_h], 0).pin_memory()          # [2, N, 3] as run_nerf.py:739 passes `batch_rays`
+    t_h = t_h.pin_memory()
+    rays_d = rays_h.to(dev)
+    t_d = t_h.to(dev)
+    weight_keys = [k for k in master if k.endswith(".weight")]
+
+    def requantize():
+        """BASELINE cfg2 'quantize' leg: float weights -> levels at qp (GPU kernel), repacked for the MLP."""
+        with torch.no_grad():
+            sd = wrapper.state_dict()
+            for k in weight_keys:
+                sd[k].copy_(master[k])
+            for k in master:
+                if k.endswith(".bias"):
+                    sd[k].copy_(master[k])
+        codec.quantize_model(wrapper, QP, QP_DENSITY, NONWEIGHT_QP)
+
+    def lsa_step(rays, target, requant):
+        if requant:
+            requantize()
+        rgb, disp, acc, extras = R.render(4, 4, None, chunk=32768, rays=rays, near=2.0, far=6.0, retraw=False, **train_kw)
+        loss = R.img2mse(rgb, target) + R.img2mse(extras["rgb0"], target)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    requantize()
+    requant_each_step = not args.no_requant
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # (1) device-resident inputs
+    ms_step = timed(lambda: lsa_step((rays_d[0], rays_d[1]), t_d, requant_each_step), args.steps, args.warmup)
+    # (2) end to end through the public API with host buffers: H2D of rays+target, D2H of the loss, every step
+    def e2e_step():
+        r = rays_h.to(dev, non_blocking=True)
+        t = t_h.to(dev, non_blocking=True)
+        loss = lsa_step((r[0], r[1]), t, requant_each_step)
+        return float(loss.detach().cpu())
+    ms_e2e = timed(e2e_step, args.steps, min(args.warmup, 3))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_norequant = timed(lambda: lsa_step((rays_d[0], rays_d[1]), t_d, False), args.steps, 3)
+
+    # (3) forward-only rendering (test-view path): rays/s through render_rays without saving activations
+    _, test_kw = R.create_nerf(wrapper, white_bkgd=True, dataset_type="blender")
+    n_view = 65536
+    ov, dv, _ = synth_batch(n_view, 77 + rank, dev)
+
+    def fwd_only():
+        with torch.no_grad():
+            R.render(4, 4, None, chunk=32768, rays=(ov, dv), near=2.0, far=6.0, **test_kw)
+    ms_view = timed(fwd_only, max(3, args.steps // 2), 3)
+
+    # (4) kernel-level timing for the roofline (live CUDA events around single launches, same sizes as the step)
+    kern = {}
+    if rank == 0:
+        pn = wrapper.model_fine.packed_net()
+        rays11 = ops.pack_rays(rays_d[0], rays_d[1], False, 4, 4, 1.0, 2.0, 6.0)
+        for name, S in (("coarse", N_SAMPLES), ("fine", N_SAMPLES + N_IMPORTANCE)):
+            z = torch.sort(2.0 + 4.0 * torch.rand(RAYS_PER_GPU, S, device=dev), -1).values.contiguous()
+            save = torch.empty(packed.mlp_save_bytes(RAYS_PER_GPU * S), dtype=torch.uint8, device=dev)
+            raw = packed.mlp_forward(pn, rays11, z, save=save, pingpong=R.TUNING["pingpong"])
+            d_raw = torch.randn_like(raw) * 1e-5
+            acc = torch.zeros(2436, device=dev)
+            kern[f"mlp_fwd_{name}"] = (timed(lambda: packed.mlp_forward(pn, rays11, z, save=save, pingpong=R.TUNING["pingpong"]), 10, 3)
+                                       if world == 1 else None, RAYS_PER_GPU * S * FLOP_PER_POINT_FWD)
+            kern[f"mlp_bwd_{name}"] = (timed(lambda: ops.mlp_backward(pn, d_raw, raw, save, acc), 10, 3) if world == 1 else None,
+                                       RAYS_PER_GPU * S * FLOP_PER_POINT_BWD)
+            kern[f"mlp_fwd_nosave_{name}"] = (timed(lambda: packed.mlp_forward(pn, rays11, z, pingpong=R.TUNING["pingpong"]), 10, 3)
+                                              if world == 1 else None, RAYS_PER_GPU * S * FLOP_PER_POINT_FWD)
+            del save
+
+    if rank == 0:
+        pk = peaks()
+        rays_s = world * RAYS_PER_GPU / (ms_step * 1e-3)
+        line = {"metric": METRIC, "value": rays_s, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+                "data": "synthetic",
+                "lsa_steps_per_sec": 1e3 / ms_step,
+                "lsa_steps_per_sec_no_requant": 1e3 / ms_norequant,
+                "render_rays_per_sec_forward_only": world * n_view / (ms_view * 1e-3),
+                "config": {"workload": "cfg2: LSA fine-tuning step at qp=-20 (quantise -> LSA-scaled dequant in the MLP epilogue -> "
+                                       "render 4096 rays/GPU, 64+128 samples -> backward into LSA scales -> Adam)",
+                           "rays_per_gpu": RAYS_PER_GPU, "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE, "qp": QP,
+                           "perturb": 1.0, "white_bkgd": True, "requantize_every_step": requant_each_step,
+                           "operands": "fp16 operands, fp32 accumulate (TMEM)", "pingpong": R.TUNING["pingpong"],
+                           "parallelism": f"dp{world}" if world > 1 else "single",
+                           "l2": "per-step working set (saved activations 5.1 GB/GPU) exceeds the 126 MB L2; no explicit flush"},
+                "e2e": {"value": world * RAYS_PER_GPU / (ms_e2e * 1e-3), "unit": "rays/s",
+                        "h2d_bytes_per_step": int(rays_h.numel() * 4 + t_h.numel() * 4), "d2h_bytes_per_step": 4},
+                "clocks": clocks}
+        # launches of OUR kernels per step: pack_rays 1, per network pass: set_scale_bias 1 + mlp_fwd 1 + composite_fwd 1,
+        # coarse_depths 1, sample_fine 1, bwd: 2 x (composite_bwd 1 + mlp_bwd 1); requantise: 24 tensors x 2 (w, b) x
+        # (absmax + quantize + dequantize) + 2 nets x 2 pack kernels
+        per_step = 1 + 2 * 3 + 1 + 1 + 2 * 2 + (24 * 2 * 3 + 4 if requant_each_step else 0)
+        line["gpu_launches"] = per_step * args.steps
+        if world == 1:
+            rows = {k: {"ms": v[0], "tflops": v[1] / (v[0] * 1e-3) / 1e12} for k, v in kern.items()}
+            step_kernel_ms = sum(rows[k]["ms"] for k in ("mlp_fwd_coarse", "mlp_fwd_fine", "mlp_bwd_coarse", "mlp_bwd_fine"))
+            dom = max(("mlp_fwd_fine", "mlp_bwd_fine"), key=lambda k: rows[k]["ms"])
+            line["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": rows[dom]["tflops"], "peak": pk["tensor"], "unit": "TFLOP/s",
+                                "frac": rows[dom]["tflops"] / pk["tensor"], "traffic": None, "peak_source": pk["source"] + " (sustained bf16)",
+                                "share_of_step": rows[dom]["ms"] / ms_norequant, "mlp_kernels_share_of_step": step_kernel_ms / ms_norequant}
+            line["kernels"] = rows
+            # CPU baseline: the oracle port on this box's host cores, bounded sample
+            try:
+                torch.set_num_threads(os.cpu_count() or 1)
+                sample = 256
+                sec, threads = cpu_lsa_steps(oracle_model(), sample, 2, 1)
+                line["cpu_baseline"] = {"value": sample / sec, "unit": "rays/s", "cores": threads, "kind": "port",
+                                        "sample": f"{sample}-ray LSA steps (fwd+bwd+Adam) of the oracle, torch CPU fp32, mean of 2 after 1 warm-up"}
+            except Exception as ex:  # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "unit": "rays/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-requant", action="store_true", help="quantise once before the loop (what the reference does)")
+    ap.add_argument("--no-pingpong", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

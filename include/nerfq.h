@@ -1,0 +1,115 @@
+/* nerfq -- C ABI of the B200-native NeRF ray-rendering hot path (libnerfq.so).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the comment says "host";
+ *   - every call is enqueued on `stream` and returns immediately (no allocation, no sync);
+ *   - return value: 0 ok, -1 bad argument, -2 kernel attribute error, -3 launch error;
+ *   - empty inputs (n == 0) are accepted and do nothing;
+ *   - tensors are dense row-major float32 / int32.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * checkout jihyounchoi/vanilla-nerf-model-compression-using-lsa-enhanced-nncodec).  The reference has
+ * no FFI of its own on the render path (it is torch eager code); its one native boundary is the
+ * pybind11 module `deepCABAC`, whose quantLayer/dequantLayer the quantiser entry points mirror.
+ */
+#ifndef NERFQ_H
+#define NERFQ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* nerfq_stream_t; /* == cudaStream_t */
+
+/* ------------------------------------------------------------------------------------------------
+ * Quantiser (replaces deepCABAC Encoder.quantLayer(dq_flag=0) / Decoder.dequantLayer)
+ *   call sites: nnc_core/approximator/baseline.py:48-57 (quantLayer), :98 (dequantLayer)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* delta(qp, qp_density): nnc_core/common.py:28-46.  `out` is a HOST pointer. */
+int nerfq_stepsize(int qp, int qp_density, float* out);
+
+/* level = sign(w) * (int)(|w|/delta + 0.5f).  The qp is raised until the largest level fits int32
+ * (baseline.py:60-62) and written to *qp_used (device int, nullable).  workspace4: 4 bytes. */
+int nerfq_quantize_urq(const float* w, int32_t* lvl, long long n, int qp, int qp_density, int* qp_used,
+                       void* workspace4, nerfq_stream_t stream);
+
+/* w = (float)level * delta(qp). */
+int nerfq_dequantize(const int32_t* lvl, float* w, long long n, int qp, int qp_density, nerfq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Packed network (replaces the NeRF / ScaledLinear parameter tensors as the MLP kernels' input)
+ *   utils.py:18-80 (NeRF), framework/applications/utils/transforms.py:84-111 (ScaledLinear)
+ * Layer order of the 12 weight pointers: pts_linears.0..7, alpha_linear, feature_linear,
+ * views_linears.0, rgb_linear.  Flat per-channel order (scale, bias, d_scale; 2436 entries):
+ * pts0..7, feature, views, alpha, rgb.
+ * ---------------------------------------------------------------------------------------------- */
+unsigned long long nerfq_packed_net_bytes(void);
+int nerfq_num_channels(void);
+
+/* weights12: HOST array of 12 device pointers ([out,in] row-major; int32 levels if src_is_int32 else float32);
+ * delta12: HOST array of the 12 step sizes (1.0 for unquantised weights). */
+int nerfq_pack_net(void* packed, const void* const* weights12, const float* delta12, int src_is_int32,
+                   nerfq_stream_t stream);
+
+/* Epilogue constants {delta*scale, bias} per output channel; scale == NULL means no LSA (scale 1). */
+int nerfq_set_scale_bias(void* packed, const float* scale, const float* bias, nerfq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused positional encoding + MLP (replaces run_network + NeRF.forward)
+ *   framework/nerf_model/run_nerf.py:46-63,408,430; run_nerf_helpers.py:18-67; utils.py:57-80
+ * rays [n_rays,11] = o(3) d(3) near far viewdir(3); z [n_rays,S]; raw [n_rays,S,4] = rgb logits, sigma.
+ * save (nullable): nerfq_mlp_save_bytes(n_rays*S) bytes receiving the activations the backward needs.
+ * pingpong: 0 = the two tiles of a CTA share every weight stage, 1 = they alternate (epilogue/MMA overlap).
+ * max_ctas: 0 = one CTA per SM.
+ * ---------------------------------------------------------------------------------------------- */
+int nerfq_mlp_forward(const void* packed, const float* rays, const float* z, long long n_rays, int samples_per_ray,
+                      float* raw, void* save, int pingpong, int max_ctas, nerfq_stream_t stream);
+unsigned long long nerfq_mlp_save_bytes(long long n_points);
+
+/* Gradient of the loss w.r.t. the LSA scales (replaces torch autograd over NeRF.forward with only
+ * weight_scaling trainable: framework/pytorch_model/__init__.py:1129-1145, run_nerf.py:756).
+ * d_scale [2436] is ACCUMULATED (caller zeroes). */
+int nerfq_mlp_backward(const void* packed, const float* d_raw, const float* raw, const void* save, long long n_points,
+                       float* d_scale, int max_ctas, nerfq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ray-side kernels
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Stratified depths, run_nerf.py:379-403.  t_rand [n_rays,S] nullable (perturb). */
+int nerfq_coarse_depths(const float* rays, const float* t_rand, long long n_rays, int S, int lindisp, float* z_out,
+                        nerfq_stream_t stream);
+
+/* raw2outputs, run_nerf.py:285-345.  noise [n_rays,S] nullable; depth, weights nullable. */
+int nerfq_composite_fwd(const float* raw, const float* z, const float* rays, const float* noise, int white_bkgd,
+                        long long n_rays, int S, float* rgb, float* disp, float* acc, float* depth, float* weights,
+                        nerfq_stream_t stream);
+
+/* d loss / d raw given d loss / d rgb_map (the only output the LSA objective uses, run_nerf.py:741-751). */
+int nerfq_composite_bwd(const float* raw, const float* z, const float* rays, const float* noise, int white_bkgd,
+                        const float* d_rgb, long long n_rays, int S, float* d_raw, nerfq_stream_t stream);
+
+/* sample_pdf (+ concat + sort + z_std), run_nerf_helpers.py:119-163 and run_nerf.py:423-429,451.
+ * Either z_coarse [n,S] (bins = midpoints; z_out [n,S+Ni] = sorted union) or bins [n,S-1] (z_out NULL).
+ * weights [n,S] (interior S-2 entries are read); u [n,Ni] nullable = deterministic linspace. */
+int nerfq_sample_fine(const float* z_coarse, const float* bins, const float* weights, const float* u, long long n_rays,
+                      int S, int Ni, float* z_out, float* z_std, float* z_samples, nerfq_stream_t stream);
+
+/* get_rays + viewdirs + ndc_rays + ray packing, run_nerf_helpers.py:71-115 and run_nerf.py:108-142.
+ * K4 = {fx, fy, cx, cy} and c2w12 (3x4 row-major) are HOST pointers. */
+int nerfq_camera_rays(int H, int W, const float* K4, const float* c2w12, int ndc, float near, float far,
+                      long long first_pixel, long long count, float* rays_out, nerfq_stream_t stream);
+int nerfq_pack_rays(const float* rays_o, const float* rays_d, long long n, int ndc, int H, int W, float focal, float near,
+                    float far, float* rays_out, nerfq_stream_t stream);
+
+/* img2mse (x2) and gradient, run_nerf_helpers.py:12 and run_nerf.py:741-751.  loss2[2] must be zeroed. */
+int nerfq_mse_grad(const float* rgb, const float* rgb0, const float* target, long long n_rays, float* d_rgb,
+                   float* d_rgb0, float* loss2, nerfq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERFQ_H */

@@ -29,6 +29,7 @@ mse2psnr = lambda x: -10. * torch.log(x) / torch.log(torch.tensor([10.], device=
 to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)
 
 TUNING = {"pingpong": True, "max_ctas": 0}      # kernel scheduling knobs (bench/profiling)
+DATA_PARALLEL = {"enabled": False}              # all-reduce (mean) the LSA-scale gradients over torch.distributed
 
 
 class _FusedQuery:
@@ -176,6 +177,9 @@ class _RenderRaysFn(torch.autograd.Function):
                 d_raw0 = ops.composite_bwd(st["raw0"], st["z0"], rays, cfg.white, d_rgb0.contiguous(), cfg.noise0)
                 ops.mlp_backward(st["pn0"], d_raw0, st["raw0"], st["save0"], g0, max_ctas=mc)
         ctx.st = None
+        if DATA_PARALLEL["enabled"]:   # one 19.5 KB all-reduce per step; the loss is a mean over the GLOBAL batch
+            from .distributed import allreduce_scale_grads
+            g0, g1 = allreduce_scale_grads(g0, g1)
         return None, g0, (g1 if ctx.has1 else None)
 
 
