@@ -11,7 +11,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
-#include "net_layout.h"
+#include "net_layout2.h"
 #include "ptx_sm100.cuh"
 
 namespace nerfq {
@@ -70,6 +70,52 @@ __global__ void pack_images_kernel(const PackParams p) {
     }
 }
 
+// ---- v2 images ("channels on lanes", net_layout2.h): stages of [128 rows x 32 k], ordered (step, half, k stage) ----
+__device__ __constant__ Step2 kFwd2Tab[kFwd2Steps] = NERFQ_FWD2_TABLE;
+__device__ __constant__ Step2 kBwd2Tab[kBwd2Steps] = NERFQ_BWD2_TABLE;
+
+__global__ void pack_images2_kernel(const PackParams p) {
+    const bool bwd = blockIdx.x >= kFwd2Stages;
+    int sidx = bwd ? blockIdx.x - kFwd2Stages : blockIdx.x;
+    const Step2* tab = bwd ? kBwd2Tab : kFwd2Tab;
+    const int nsteps = bwd ? kBwd2Steps : kFwd2Steps;
+    uint8_t* dst = p.packed + (bwd ? kOffBwd2Image : kOffFwd2Image) + (size_t)sidx * kStage2Bytes;
+    int s = 0;
+    for (; s < nsteps; ++s) {
+        const int n = tab[s].halves * (tab[s].kh + tab[s].kp);
+        if (sidx < n) break;
+        sidx -= n;
+    }
+    const Step2 st = tab[s];
+    const int per_half = st.kh + st.kp;
+    const int mh = sidx / per_half, j = sidx % per_half;
+    const int in = kInDev[st.layer], out = kOutDev[st.layer];
+    for (int item = threadIdx.x; item < 128 * 4; item += blockDim.x) {
+        const int r = item >> 2, chunk = item & 3;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float x = 0.0f;
+            if (!bwd) {
+                // forward: A[r][kk] = W[o = 128 mh + r][col], col from the activation part or the encoding part
+                const int o = 128 * mh + r;
+                int kk, col0, valid;
+                if (j < st.kh) { kk = j * 32 + chunk * 8 + e; col0 = st.hcol0; valid = st.hvalid; }
+                else { kk = (j - st.kh) * 32 + chunk * 8 + e; col0 = st.pcol0; valid = st.pvalid; }
+                if (o < out && kk < valid) x = load_w(p, st.layer, o * in + col0 + kk);
+            } else {
+                // backward: A[r][kk] = W[o = 32 j + kk][hcol0 + 128 mh + r]
+                const int o = j * 32 + chunk * 8 + e;
+                if (o < st.hvalid && o < out) x = load_w(p, st.layer, o * in + st.hcol0 + 128 * mh + r);
+            }
+            v[e] = x;
+        }
+        uint4 q;
+        q.x = pack_half2(v[0], v[1]); q.y = pack_half2(v[2], v[3]); q.z = pack_half2(v[4], v[5]); q.w = pack_half2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(dst + sw64_offset(r, chunk)) = q;
+    }
+}
+
 // per-channel delta, and the alpha / rgb head weights as float levels
 __global__ void pack_small_kernel(const PackParams p) {
     float* delta = reinterpret_cast<float*>(p.packed + kOffDelta);
@@ -103,7 +149,7 @@ __global__ void set_scale_bias_kernel(uint8_t* packed, const float* __restrict__
 
 }  // namespace nerfq
 
-extern "C" unsigned long long nerfq_packed_net_bytes(void) { return nerfq::kPackedBytes; }
+extern "C" unsigned long long nerfq_packed_net_bytes(void) { return nerfq::kPacked2Bytes; }
 extern "C" int nerfq_num_channels(void) { return nerfq::kNumChannels; }
 
 extern "C" int nerfq_pack_net(void* packed, const void* const* weights12, const float* delta12, int src_is_int32,
@@ -119,6 +165,7 @@ extern "C" int nerfq_pack_net(void* packed, const void* const* weights12, const 
     p.packed = reinterpret_cast<uint8_t*>(packed);
     p.src_is_int32 = src_is_int32;
     pack_images_kernel<<<kFwdStages + kBwdStages, 256, 0, stream>>>(p);
+    pack_images2_kernel<<<kFwd2Stages + kBwd2Stages, 256, 0, stream>>>(p);
     pack_small_kernel<<<8, 256, 0, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
