@@ -76,7 +76,7 @@ class PackedNet:
         return self.buf.data_ptr()
 
 
-IMPL = {"version": 2}      # 2: channels-on-lanes kernels (mlp2_*.cu); 1: first-generation kernels (mlp_*.cu)
+IMPL = {"version": 1}      # 2: channels-on-lanes kernels (mlp2_*.cu); 1: first-generation kernels (mlp_*.cu)
 
 
 def mlp_save_bytes(n_points: int, impl: Optional[int] = None) -> int:
