@@ -1,0 +1,45 @@
+"""Per-CTA cycle counters of the v3 fused MLP forward kernel (where the MMA issuer and one epilogue warp wait)."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import nerfq_b200  # noqa
+from nerfq_b200 import _lib, codec, model as nmodel, ops, packed
+
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+w = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params().to(dev)
+codec.quantize_model(w, -20)
+pn = w.model_fine.packed_net()
+pn.set_scales(w.model_fine.scale_tensors())
+n, S = 4096, 192
+g = torch.Generator().manual_seed(2)
+o = 0.1 * torch.randn(n, 3, generator=g) + torch.tensor([0.0, 0.0, 4.0])
+d = torch.randn(n, 3, generator=g)
+d = -d / d.norm(dim=-1, keepdim=True)
+rays = ops.pack_rays(o.to(dev), d.to(dev), False, 4, 4, 1.0, 2.0, 6.0)
+z = torch.sort(2.0 + 4.0 * torch.rand(n, S, device=dev), -1).values.contiguous()
+L = _lib.lib()
+L.nerfq_mlp3_set_debug.argtypes = [ctypes.c_void_p, ctypes.c_int]
+L.nerfq_mlp3_set_debug.restype = None
+buf = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+save = torch.empty(packed.mlp_save_bytes(n * S, impl=3), dtype=torch.uint8, device=dev)
+for mode, kw, flags in (("nosave", {}, 0), ("save", {"save": save}, 0), ("nosave, no epilogue math", {}, 1),
+                        ("nosave, no epilogue, no copies", {}, 5), ("nosave, no epilogue, no MMA", {}, 3),
+                        ("nosave, control only", {}, 7)):
+    for _ in range(2):
+        packed.mlp_forward(pn, rays, z, impl=3, **kw)
+    L.nerfq_mlp3_set_debug(buf.data_ptr(), flags)
+    buf.zero_()
+    packed.mlp_forward(pn, rays, z, impl=3, **kw)
+    torch.cuda.synchronize()
+    L.nerfq_mlp3_set_debug(None, 0)
+    t = buf.cpu().numpy().reshape(148, 8).astype(np.float64)
+    groups = (n * S // 256 + 147) // 148
+    print(f"{mode}: per CTA (mean over CTAs), {groups} groups: total {t[:,0].mean():.0f} cyc = {t[:,0].mean()/groups:.0f}/group "
+          f"(ideal MMA 38400/group); issuer waits: WFull {t[:,1].mean()/groups:.0f}  ActLo {t[:,2].mean()/groups:.0f}  ActHi {t[:,3].mean()/groups:.0f}; "
+          f"epilogue warp waits: AccReady {t[:,4].mean()/groups:.0f}  StageFree {t[:,5].mean()/groups:.0f}")

@@ -1,4 +1,4 @@
-"""GPU-box debug script for the v2 ("channels on lanes") forward kernel: per-layer errors from the saved
+"""GPU-box debug script for the v3 ("channels on lanes") forward kernel: per-layer errors from the saved
 MN-major operand images, raw output error, timing."""
 import os
 import sys
@@ -35,8 +35,8 @@ def main():
     rays = synth_rays(n_rays, 11)
     z = ro.coarse_depths(rays[:, 6:7], rays[:, 7:8], S).contiguous()
     M = n_rays * S
-    save = torch.zeros(packed.mlp_save_bytes(M, impl=2), dtype=torch.uint8, device=dev)
-    raw = packed.mlp_forward(pn, rays.to(dev), z.to(dev), save=save, impl=2)
+    save = torch.zeros(packed.mlp_save_bytes(M, impl=3), dtype=torch.uint8, device=dev)
+    raw = packed.mlp_forward(pn, rays.to(dev), z.to(dev), save=save, impl=3)
     torch.cuda.synchronize()
     raw = raw.cpu().reshape(-1, 4)
     pts = (rays[:, None, 0:3] + rays[:, None, 3:6] * z[:, :, None]).reshape(-1, 3)
@@ -45,7 +45,7 @@ def main():
         hs, feat, hv, raw_ref = oracle_intermediates(p, "model", pts, vd)
     buf = save.cpu().numpy()
     groups = (M + 255) // 256
-    print(f"--- v2 forward: points={M} groups={groups}")
+    print(f"--- v3 forward: points={M} groups={groups}")
     for slot, (nm, ref) in enumerate(zip(["h1", "h2", "h3", "h4", "h5", "h6", "h7", "h8", "feat"], hs + [feat])):
         got = np.concatenate([decode_image(buf, g, slot, 256) for g in range(groups)], 0)[:M]
         err = np.abs(got - ref.numpy())
@@ -54,16 +54,16 @@ def main():
     print(f"  hv: maxerr={np.abs(got - hv.numpy()).max():.5f}")
     err = (raw - raw_ref).abs()
     print(f"  raw: max|ref|={raw_ref.abs().max():.4f} maxerr={err.max():.5f} per-channel {err.max(0).values.tolist()}")
-    raw2 = packed.mlp_forward(pn, rays.to(dev), z.to(dev), impl=2).cpu().reshape(-1, 4)
+    raw2 = packed.mlp_forward(pn, rays.to(dev), z.to(dev), impl=3).cpu().reshape(-1, 4)
     print("  save vs nosave identical:", bool((raw2 == raw).all()), " finite:", bool(torch.isfinite(raw).all()))
     raw1 = packed.mlp_forward(pn, rays.to(dev), z.to(dev), impl=1, pingpong=True).cpu().reshape(-1, 4)
-    print("  v1 vs v2 max diff:", float((raw1 - raw).abs().max()))
+    print("  v1 vs v3 max diff:", float((raw1 - raw).abs().max()))
     n_rays = 16384
     rays = synth_rays(n_rays, 12).to(dev)
     for S in (64, 192):
         z = torch.sort(2.0 + 4.0 * torch.rand(n_rays, S, device=dev), -1).values.contiguous()
-        save = torch.empty(packed.mlp_save_bytes(n_rays * S, impl=2), dtype=torch.uint8, device=dev)
-        for name, kw in (("v2 nosave", dict(impl=2)), ("v2 save", dict(impl=2, save=save)), ("v1 pingpong nosave", dict(impl=1, pingpong=True))):
+        save = torch.empty(packed.mlp_save_bytes(n_rays * S, impl=3), dtype=torch.uint8, device=dev)
+        for name, kw in (("v3 nosave", dict(impl=3)), ("v3 save", dict(impl=3, save=save)), ("v1 pingpong nosave", dict(impl=1, pingpong=True))):
             for _ in range(2):
                 packed.mlp_forward(pn, rays, z, **kw)
             torch.cuda.synchronize()

@@ -11,7 +11,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
-#include "net_layout2.h"
+#include "mlp3_layout.h"
 #include "ptx_sm100.cuh"
 
 namespace nerfq {
@@ -70,23 +70,27 @@ __global__ void pack_images_kernel(const PackParams p) {
     }
 }
 
-// ---- v2 images ("channels on lanes", net_layout2.h): stages of [128 rows x 32 k], ordered (step, half, k stage) ----
-__device__ __constant__ Step2 kFwd2Tab[kFwd2Steps] = NERFQ_FWD2_TABLE;
-__device__ __constant__ Step2 kBwd2Tab[kBwd2Steps] = NERFQ_BWD2_TABLE;
+// ---- v3 images ("channels on lanes", mlp3_layout.h): stages of [128 rows x 32 k] in consumption order
+// (step, half, k stage); two consecutive stages form one 16 KB chunk ----
+struct Step3Tables {
+    Step3 fwd[kFwd3Steps];
+    Step3 bwd[kBwd3Steps];
+};
 
-__global__ void pack_images2_kernel(const PackParams p) {
-    const bool bwd = blockIdx.x >= kFwd2Stages;
-    int sidx = bwd ? blockIdx.x - kFwd2Stages : blockIdx.x;
-    const Step2* tab = bwd ? kBwd2Tab : kFwd2Tab;
-    const int nsteps = bwd ? kBwd2Steps : kFwd2Steps;
-    uint8_t* dst = p.packed + (bwd ? kOffBwd2Image : kOffFwd2Image) + (size_t)sidx * kStage2Bytes;
+__global__ void pack_images3_kernel(const PackParams p, const Step3Tables tabs) {
+    const int n_fwd = 2 * kFwd3Chunks;
+    const bool bwd = (int)blockIdx.x >= n_fwd;
+    int sidx = bwd ? blockIdx.x - n_fwd : blockIdx.x;
+    const Step3* tab = bwd ? tabs.bwd : tabs.fwd;
+    const int nsteps = bwd ? kBwd3Steps : kFwd3Steps;
+    uint8_t* dst = p.packed + (bwd ? kOffBwd3Image : kOffFwd3Image) + (size_t)sidx * kStage3Bytes;
     int s = 0;
     for (; s < nsteps; ++s) {
         const int n = tab[s].halves * (tab[s].kh + tab[s].kp);
         if (sidx < n) break;
         sidx -= n;
     }
-    const Step2 st = tab[s];
+    const Step3 st = tab[s];
     const int per_half = st.kh + st.kp;
     const int mh = sidx / per_half, j = sidx % per_half;
     const int in = kInDev[st.layer], out = kOutDev[st.layer];
@@ -99,10 +103,20 @@ __global__ void pack_images2_kernel(const PackParams p) {
             if (!bwd) {
                 // forward: A[r][kk] = W[o = 128 mh + r][col], col from the activation part or the encoding part
                 const int o = 128 * mh + r;
-                int kk, col0, valid;
-                if (j < st.kh) { kk = j * 32 + chunk * 8 + e; col0 = st.hcol0; valid = st.hvalid; }
-                else { kk = (j - st.kh) * 32 + chunk * 8 + e; col0 = st.pcol0; valid = st.pvalid; }
-                if (o < out && kk < valid) x = load_w(p, st.layer, o * in + col0 + kk);
+                int col = -1;
+                if (j < st.kh) {
+                    const int kk = j * 32 + chunk * 8 + e;
+                    if (kk < st.hvalid) col = st.hcol0 + kk;
+                } else {
+                    const int kk = (j - st.kh) * 32 + chunk * 8 + e;
+                    if (st.pvalid == 63) {                     // gamma(x): rotated column order of the encoding tile
+                        const int src = kk < 64 ? pe_source_col(kk) : -1;
+                        if (src >= 0) col = st.pcol0 + src;
+                    } else if (kk < st.pvalid) {
+                        col = st.pcol0 + kk;
+                    }
+                }
+                if (o < out && col >= 0) x = load_w(p, st.layer, o * in + col);
             } else {
                 // backward: A[r][kk] = W[o = 32 j + kk][hcol0 + 128 mh + r]
                 const int o = j * 32 + chunk * 8 + e;
@@ -149,7 +163,7 @@ __global__ void set_scale_bias_kernel(uint8_t* packed, const float* __restrict__
 
 }  // namespace nerfq
 
-extern "C" unsigned long long nerfq_packed_net_bytes(void) { return nerfq::kPacked2Bytes; }
+extern "C" unsigned long long nerfq_packed_net_bytes(void) { return nerfq::kPacked3Bytes; }
 extern "C" int nerfq_num_channels(void) { return nerfq::kNumChannels; }
 
 extern "C" int nerfq_pack_net(void* packed, const void* const* weights12, const float* delta12, int src_is_int32,
@@ -165,7 +179,10 @@ extern "C" int nerfq_pack_net(void* packed, const void* const* weights12, const 
     p.packed = reinterpret_cast<uint8_t*>(packed);
     p.src_is_int32 = src_is_int32;
     pack_images_kernel<<<kFwdStages + kBwdStages, 256, 0, stream>>>(p);
-    pack_images2_kernel<<<kFwd2Stages + kBwd2Stages, 256, 0, stream>>>(p);
+    Step3Tables tabs;
+    for (int i = 0; i < kFwd3Steps; ++i) tabs.fwd[i] = kFwd3[i];
+    for (int i = 0; i < kBwd3Steps; ++i) tabs.bwd[i] = kBwd3[i];
+    pack_images3_kernel<<<2 * (kFwd3Chunks + kBwd3Chunks), 256, 0, stream>>>(p, tabs);
     pack_small_kernel<<<8, 256, 0, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

@@ -43,17 +43,30 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
 #ifndef NERFQ_MBAR_SPIN_LIMIT
-#define NERFQ_MBAR_SPIN_LIMIT (1u << 26)
+#define NERFQ_MBAR_SPIN_LIMIT (1u << 20)
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > NERFQ_MBAR_SPIN_LIMIT) {
+        if (++spins > (threadIdx.x < 128 ? NERFQ_MBAR_SPIN_LIMIT / 8 : NERFQ_MBAR_SPIN_LIMIT)) {   // control warps report first
             printf("nerfq: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
             __trap();
         }
     }
 }
+
+// One lane of a converged warp (the compiler keeps warp-uniform operands of the elected code in uniform registers).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// warp index as a provably warp-uniform value
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 
 // ------------------------------------------------------------------------------------------
 // proxies / fences

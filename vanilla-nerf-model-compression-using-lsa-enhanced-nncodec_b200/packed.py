@@ -76,13 +76,13 @@ class PackedNet:
         return self.buf.data_ptr()
 
 
-IMPL = {"version": 1}      # 2: channels-on-lanes kernels (mlp2_*.cu); 1: first-generation kernels (mlp_*.cu)
+IMPL = {"version": 1}      # 3: channels-on-lanes kernels (mlp3_*.cu); 1: first-generation kernels (mlp_*.cu)
 
 
 def mlp_save_bytes(n_points: int, impl: Optional[int] = None) -> int:
     impl = IMPL["version"] if impl is None else impl
-    if impl == 2:
-        return int(_lib.lib().nerfq_mlp2_save_bytes(n_points))
+    if impl == 3:
+        return int(_lib.lib().nerfq_mlp3_save_bytes(n_points))
     return int(_lib.lib().nerfq_mlp_save_bytes(n_points))
 
 
@@ -94,10 +94,10 @@ def mlp_forward(net: PackedNet, rays: torch.Tensor, z: torch.Tensor, save: Optio
     n, s = z.shape
     raw = torch.empty((n, s, 4), dtype=torch.float32, device=rays.device)
     impl = IMPL["version"] if impl is None else impl
-    if impl == 2:
-        _lib.check(_lib.lib().nerfq_mlp2_forward(net.ptr, rays.data_ptr(), z.data_ptr(), n, s, raw.data_ptr(),
+    if impl == 3:
+        _lib.check(_lib.lib().nerfq_mlp3_forward(net.ptr, rays.data_ptr(), z.data_ptr(), n, s, raw.data_ptr(),
                                                  save.data_ptr() if save is not None else None, max_ctas, _stream()),
-                   "nerfq_mlp2_forward")
+                   "nerfq_mlp3_forward")
         return raw
     _lib.check(_lib.lib().nerfq_mlp_forward(net.ptr, rays.data_ptr(), z.data_ptr(), n, s, raw.data_ptr(),
                                             save.data_ptr() if save is not None else None, int(pingpong), max_ctas,
