@@ -24,22 +24,24 @@ d = -d / d.norm(dim=-1, keepdim=True)
 rays = ops.pack_rays(o.to(dev), d.to(dev), False, 4, 4, 1.0, 2.0, 6.0)
 z = torch.sort(2.0 + 4.0 * torch.rand(n, S, device=dev), -1).values.contiguous()
 L = _lib.lib()
-L.nerfq_mlp3_set_debug.argtypes = [ctypes.c_void_p, ctypes.c_int]
-L.nerfq_mlp3_set_debug.restype = None
-buf = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+L.nerfq_mlp3_set_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
+L.nerfq_mlp3_set_trace.restype = None
+buf = torch.zeros(148 * 8 + 148 * 32, dtype=torch.int64, device=dev)
 save = torch.empty(packed.mlp_save_bytes(n * S, impl=3), dtype=torch.uint8, device=dev)
-for mode, kw, flags in (("nosave", {}, 0), ("save", {"save": save}, 0), ("nosave, no epilogue math", {}, 1),
-                        ("nosave, no epilogue, no copies", {}, 5), ("nosave, no epilogue, no MMA", {}, 3),
-                        ("nosave, control only", {}, 7)):
+for mode, kw, flags in ([("nosave", {}, 0), ("save", {"save": save}, 0)] +
+                        [(f"nosave, job {j} timed", {}, j << 8) for j in (0, 1, 2, 3, 8, 9, 14, 15, 18, 19)] +
+                        [(f"nosave, none of the three, job {j} timed", {}, 7 | (j << 8)) for j in (2, 3)]):
     for _ in range(2):
         packed.mlp_forward(pn, rays, z, impl=3, **kw)
-    L.nerfq_mlp3_set_debug(buf.data_ptr(), flags)
+    L.nerfq_mlp3_set_trace(buf.data_ptr(), flags)
     buf.zero_()
     packed.mlp_forward(pn, rays, z, impl=3, **kw)
     torch.cuda.synchronize()
-    L.nerfq_mlp3_set_debug(None, 0)
-    t = buf.cpu().numpy().reshape(148, 8).astype(np.float64)
+    L.nerfq_mlp3_set_trace(None, 0)
+    t = buf.cpu().numpy()[:148 * 8].reshape(148, 8).astype(np.float64)
     groups = (n * S // 256 + 147) // 148
-    print(f"{mode}: per CTA (mean over CTAs), {groups} groups: total {t[:,0].mean():.0f} cyc = {t[:,0].mean()/groups:.0f}/group "
-          f"(ideal MMA 38400/group); issuer waits: WFull {t[:,1].mean()/groups:.0f}  ActLo {t[:,2].mean()/groups:.0f}  ActHi {t[:,3].mean()/groups:.0f}; "
-          f"epilogue warp waits: AccReady {t[:,4].mean()/groups:.0f}  StageFree {t[:,5].mean()/groups:.0f}")
+    w = buf.cpu().numpy()[148 * 8:].reshape(148, 32).astype(np.float64).mean(0) / groups
+    m = t.mean(0) / groups
+    print(f"{mode}: per group: total {m[0]:.0f} cyc (ideal MMA 38144); issuer waits: WFull {m[1]:.0f}  ActLo {m[2]:.0f}  ActHi {m[3]:.0f}; "
+          f"epilogue warp 5: wait AccReady {m[4]:.0f}  StageFree {m[5]:.0f}  jobs {m[6]:.0f} (load+math+store part {m[7]:.0f}); "
+          f"timed job: {w[0]:.0f} cycles, of which load+math+store {w[1]:.0f}")

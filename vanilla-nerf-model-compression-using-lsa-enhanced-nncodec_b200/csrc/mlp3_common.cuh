@@ -93,9 +93,12 @@ __device__ __forceinline__ void loader3(uint32_t sbase, const uint8_t* img, int 
 // last MMA of a chunk and the first MMA of the next (commit, ring wait, descriptor bump) has to stay short.
 // `first_lo_wait`: the forward kernel's first group waits for the initial encodings (later groups get them with the
 // ActLo arrival the rgb step already consumed).
-template <int kHalves>
+// kTrace: accumulate cycle counters {total, wait WFull, wait ActLo, wait ActHi} into dbg[8*blockIdx.x + 0..3].
+template <int kHalves, bool kTrace = false>
 __device__ __forceinline__ void issuer3(uint32_t sbase, uint32_t tmem_base, const Half3* __restrict__ prog, int n_iters,
-                                        bool first_lo_wait) {
+                                        bool first_lo_wait, unsigned long long* dbg = nullptr) {
+    unsigned long long t_w = 0, t_lo = 0, t_hi = 0, t_begin = 0;
+    if (kTrace) t_begin = clock64();
     const uint32_t bar0 = sbase + kS3Bars;
     const uint64_t a_desc0 = umma_smem_desc(sbase + kS3Ring, 512, SWZ_64B);
     const uint64_t b_act0 = umma_desc_mn3(sbase + kS3Act);
@@ -107,8 +110,11 @@ __device__ __forceinline__ void issuer3(uint32_t sbase, uint32_t tmem_base, cons
                      uint32_t commit_a, uint32_t commit_b) {
         const uint32_t slot = seq & (kSlots3 - 1), par = (seq >> 2) & 1;
         ++seq;
+        unsigned long long t0 = 0;
+        if (kTrace) t0 = clock64();
         mbar_wait(bar0 + 8 * (kB3WFull + slot), par);
         tc_fence_after_sync();
+        if (kTrace) t_w += clock64() - t0;
         if (elect_one()) {
             const uint64_t ad = a_desc0 + slot * (kChunk3Bytes >> 4);
             umma_ss(d_tmem, ad, b, idesc, accumulate);
@@ -135,23 +141,32 @@ __device__ __forceinline__ void issuer3(uint32_t sbase, uint32_t tmem_base, cons
             const uint32_t d_tmem = tmem_base + (hi ? 256u : 0u);
             const uint32_t acc_bar = bar0 + 8 * (kB3AccReady + (hi ? 1 : 0));
             if (f & HS_WAIT_LO) {
+                unsigned long long t0 = 0;
+                if (kTrace) t0 = clock64();
                 mbar_wait(bar0 + 8 * kB3ActLo, ph_lo);
                 ph_lo ^= 1;
                 tc_fence_after_sync();
+                if (kTrace) t_lo += clock64() - t0;
             }
             if (f & HS_WAIT_HI_AT0) {
+                unsigned long long t0 = 0;
+                if (kTrace) t0 = clock64();
                 mbar_wait(bar0 + 8 * kB3ActHi, ph_hi);
                 ph_hi ^= 1;
                 tc_fence_after_sync();
+                if (kTrace) t_hi += clock64() - t0;
             }
             const int n_act = hs.n_act, n_enc = hs.n_enc;
             uint64_t b = b_act0;
 #pragma unroll 1
             for (int j = 0; j < n_act; ++j) {
                 if (j == 2 && (f & HS_WAIT_HI_AT2)) {
+                    unsigned long long t0 = 0;
+                    if (kTrace) t0 = clock64();
                     mbar_wait(bar0 + 8 * kB3ActHi, ph_hi);
                     ph_hi ^= 1;
                     tc_fence_after_sync();
+                    if (kTrace) t_hi += clock64() - t0;
                 }
                 const uint32_t sf = ((f & HS_SF) && j < 2) ? bar0 + 8 * (kB3StageFree + j) : 0u;
                 const uint32_t done = (j + 1 == n_act && n_enc == 0) ? acc_bar : 0u;
@@ -160,6 +175,12 @@ __device__ __forceinline__ void issuer3(uint32_t sbase, uint32_t tmem_base, cons
             }
             if (n_enc) chunk(d_tmem, b_enc0, kIdesc3BK, 32u >> 4, 64u >> 4, n_act > 0 ? 1u : 0u, 0u, acc_bar);
         }
+    }
+    if (kTrace && dbg && (threadIdx.x & 31) == 0) {
+        dbg[8 * blockIdx.x + 0] = clock64() - t_begin;
+        dbg[8 * blockIdx.x + 1] = t_w;
+        dbg[8 * blockIdx.x + 2] = t_lo;
+        dbg[8 * blockIdx.x + 3] = t_hi;
     }
 }
 
@@ -184,21 +205,18 @@ __device__ __forceinline__ void encode5(const float p[3], float scale, float* ou
     }
 }
 
-// Write 32 fp16 columns [col0, col0+32) of row `row` of the K-major SWIZZLE_128B encoding tile.
-__device__ __forceinline__ void write_enc32(uint8_t* enc, int row, int col0, const float (&v)[32]) {
+// Write 32 fp16 columns [col0, col0+32) of row `row` of the K-major SWIZZLE_128B encoding tile (shared address `enc`).
+__device__ __forceinline__ void write_enc32(uint32_t enc, int row, int col0, const float (&v)[32]) {
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
-        uint4 q;
-        q.x = pack_half2(v[8 * ch + 0], v[8 * ch + 1]);
-        q.y = pack_half2(v[8 * ch + 2], v[8 * ch + 3]);
-        q.z = pack_half2(v[8 * ch + 4], v[8 * ch + 5]);
-        q.w = pack_half2(v[8 * ch + 6], v[8 * ch + 7]);
-        *reinterpret_cast<uint4*>(enc + sw128_offset(row, (col0 >> 3) + ch)) = q;
+        st_shared_v4(enc + sw128_offset(row, (col0 >> 3) + ch), cvt_pack_f16(v[8 * ch + 0], v[8 * ch + 1]),
+                     cvt_pack_f16(v[8 * ch + 2], v[8 * ch + 3]), cvt_pack_f16(v[8 * ch + 4], v[8 * ch + 5]),
+                     cvt_pack_f16(v[8 * ch + 6], v[8 * ch + 7]));
     }
 }
 
 // gamma(x) half: role 0 -> columns 0..31 = [y, z, levels 0..4]; role 1 -> columns 32..63 = [levels 5..9, x, 0]
-__device__ __forceinline__ void write_pe_half(uint8_t* enc, int row, int role, const float p[3]) {
+__device__ __forceinline__ void write_pe_half(uint32_t enc, int row, int role, const float p[3]) {
     float v[32];
     if (role == 0) {
         v[0] = p[1]; v[1] = p[2];
@@ -211,7 +229,7 @@ __device__ __forceinline__ void write_pe_half(uint8_t* enc, int row, int role, c
 }
 
 // gamma(d): 27 values (d, then 4 levels) + 5 zeros into columns 0..31
-__device__ __forceinline__ void write_dir_enc(uint8_t* enc, int row, const float d[3]) {
+__device__ __forceinline__ void write_dir_enc(uint32_t enc, int row, const float d[3]) {
     float v[32];
     v[0] = d[0]; v[1] = d[1]; v[2] = d[2];
 #pragma unroll
@@ -259,6 +277,29 @@ __device__ __forceinline__ float column_reduce32_3(float (&p)[32], int lane) {
     }
     const bool hi = lane & 1;
     return (hi ? q2[1] : q2[0]) + __shfl_xor_sync(0xffffffffu, hi ? q2[0] : q2[1], 1);
+}
+
+// Sum each of 16 per-lane columns over the 32 lanes of the warp; lanes 2j and 2j+1 both return column j.
+__device__ __forceinline__ float column_reduce16_3(float (&p)[16], int lane) {
+    float q8[8], q4[4], q2[2];
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q8[i] = (hi ? p[i + 8] : p[i]) + __shfl_xor_sync(0xffffffffu, hi ? p[i] : p[i + 8], 16);
+    }
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q4[i] = (hi ? q8[i + 4] : q8[i]) + __shfl_xor_sync(0xffffffffu, hi ? q8[i] : q8[i + 4], 8);
+    }
+    {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) q2[i] = (hi ? q4[i + 2] : q4[i]) + __shfl_xor_sync(0xffffffffu, hi ? q4[i] : q4[i + 2], 4);
+    }
+    const bool hi = lane & 2;
+    const float r = (hi ? q2[1] : q2[0]) + __shfl_xor_sync(0xffffffffu, hi ? q2[0] : q2[1], 2);
+    return r + __shfl_xor_sync(0xffffffffu, r, 1);
 }
 
 }  // namespace nerfq

@@ -31,10 +31,12 @@ struct Fwd3Params {
     long long n_points;
     int samples_per_ray;
     int n_groups;
+    unsigned long long* dbg;     // tracing build only: 8 cycle counters per CTA
+    int dbg_flags;               // tracing build only: 1 skip TMEM loads, 2 skip operand stores, 4 skip conversion math
     Prog3Fwd prog;
 };
 
-template <bool kSave>
+template <bool kSave, bool kTrace>
 __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid_constant__ Fwd3Params prm) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -52,19 +54,23 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
     if (warp == 0) {
         loader3(sbase, prm.packed + kOffFwd3Image, kFwd3Chunks, n_iters);
     } else if (warp == 1) {
-        if (n_iters > 0) issuer3<kFwd3Jobs>(sbase, tmem_base, prm.prog.half, n_iters, true);
+        if (n_iters > 0) issuer3<kFwd3Jobs, kTrace>(sbase, tmem_base, prm.prog.half, n_iters, true, prm.dbg);
     } else if (warp >= kCtrlWarps3) {
         // ================= epilogue warps =================
         const int e = warp - kCtrlWarps3;
         const int q = e & 3, pq = e >> 2;
         const uint32_t tmem_lane = tmem_base + (uint32_t(q * 32) << 16) + pq * 64;
-        uint8_t* act = smem + kS3Act;
-        uint8_t* enc = smem + kS3Enc;
+        const uint32_t act = sbase + kS3Act;      // shared-space addresses
+        const uint32_t enc = sbase + kS3Enc;
+        const uint32_t out_sa = sbase + kS3Misc;
         const float2* g_sb = reinterpret_cast<const float2*>(prm.packed + kOffSB);
         const float* g_wa = reinterpret_cast<const float*>(prm.packed + kOffWAlpha);
         // the point whose encodings this thread (co-)writes: two threads per point for gamma(x)
         const int pt = (e >> 1) * 32 + lane, role = e & 1;
         uint32_t ph_acc0 = 0, ph_acc1 = 0, ph_sf = 0;
+        unsigned long long t_acc = 0, t_sf = 0, t_job = 0, t_math = 0, t_sel = 0, t_sel_math = 0;
+        const int j_sel = prm.dbg_flags >> 8;
+        const bool tracing = kTrace && e == 5 && lane == 0;
 
         auto publish = [&](int which) {
             fence_proxy_async_smem();
@@ -72,8 +78,8 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(which));
         };
-        float p[3], vd[3];
-        auto load_point = [&](int g) {
+        float p[3], vd[3], vd_next[3];
+        auto load_point = [&](int g, float* vdir) {
             const long long gidx = (long long)g * kGroupPts + pt;
             const long long gc = gidx < prm.n_points ? gidx : prm.n_points - 1;
             const long long ray = gc / prm.samples_per_ray;
@@ -82,32 +88,46 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 p[k] = fmaf(__ldg(r + 3 + k), zz, __ldg(r + k));
-                vd[k] = __ldg(r + 8 + k);
+                vdir[k] = __ldg(r + 8 + k);
             }
         };
+        auto load_consts = [&](int j, float2& c, float& wa) {      // epilogue constants of job j for this thread's channel
+            const Job3 jn = prm.prog.job[j];
+            c = make_float2(0.f, 0.f);
+            wa = 0.0f;
+            if (!(jn.flags & JB_FINAL)) c = __ldg(&g_sb[jn.ch + 32 * q + lane]);
+            if (jn.flags & JB_ALPHA) wa = __ldg(&g_wa[((jn.flags & JB_HI_HALF) ? 128 : 0) + 32 * q + lane]);
+        };
 
+        float2 c_next = make_float2(0.f, 0.f);
+        float wa_next = 0.0f;
         if (n_iters > 0) {
-            load_point(first);
+            load_point(first, vd);
             write_pe_half(enc, pt, role, p);
             publish(kB3ActLo);        // initial encodings
             publish(kB3ActHi);        // D_hi is free at kernel start
+            load_consts(0, c_next, wa_next);
         }
         for (int g = first; g < prm.n_groups; g += stride) {
             uint8_t* save_g = kSave ? prm.save + (size_t)g * kSave3GroupBytes : nullptr;
+            // the next group's point is fetched now so that its encoding can be written the moment the tile is free
+            if (g + stride < prm.n_groups) load_point(g + stride, vd_next);
 #pragma unroll 1
             for (int j = 0; j < kFwd3Jobs; ++j) {
                 const Job3 jb = prm.prog.job[j];
                 const uint32_t f = jb.flags;
                 const uint32_t hi = (f & JB_HI_HALF) ? 1u : 0u;
                 const uint32_t ch = 128u * hi + 32u * q + lane;              // this thread's channel within the layer
-                float2 c = make_float2(0.f, 0.f);
-                float wa = 0.0f;
-                if (!(f & JB_FINAL)) c = __ldg(&g_sb[jb.ch + 32 * q + lane]);
-                if (f & JB_ALPHA) wa = __ldg(&g_wa[ch]);
+                const float2 c = c_next;
+                const float wa = wa_next;
+                unsigned long long t0 = 0;
+                if (tracing) t0 = clock64();
                 if (f & JB_ACC_HI) { mbar_wait(bar(kB3AccReady + 1), ph_acc1); ph_acc1 ^= 1; }
                 else { mbar_wait(bar(kB3AccReady + 0), ph_acc0); ph_acc0 ^= 1; }
                 tc_fence_after_sync();
+                if (tracing) { const unsigned long long t1 = clock64(); t_acc += t1 - t0; t0 = t1; }
                 const uint32_t ta = tmem_lane + ((f & JB_ACC_HI) ? 256u : 0u);
+                load_consts(j + 1 < kFwd3Jobs ? j + 1 : 0, c_next, wa_next);    // in flight during this job
 
                 if (f & JB_FINAL) {
                     // rgb head: lanes 0..2 of the accumulator hold the three logit rows; sigma comes from the alpha
@@ -129,59 +149,77 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                                 }
                             }
                             const int pl = pq * 64 + cc * 32 + lane;
-                            const float sg = fmaf(out_s[pl], ca.x, ca.y);
-                            out_s[pl] = 0.0f;
+                            const float sg = fmaf(ld_shared_f32(out_sa + 4 * pl), ca.x, ca.y);
+                            st_shared_f32(out_sa + 4 * pl, 0.0f);
                             const long long gi = g0 + cc * 32 + lane;
                             if (gi < prm.n_points) prm.raw[4 * gi + 3] = sg;
                         }
                     }
                     publish(kB3ActHi);
+                    if (tracing) { const unsigned long long dt = clock64() - t0; t_job += dt; if (j == j_sel) t_sel += dt; }
                     continue;
                 }
 
                 if (f & JB_DIR_BEFORE) {        // gamma(x) is dead once L5 has been accumulated
                     if (role == 0) write_dir_enc(enc, pt, vd);
                 }
-                // ---- 2 chunks of 32 points: TMEM -> y = acc*es + b -> (ReLU) -> fp16 ----
-                const float lo_clamp = (f & JB_RELU) ? 0.0f : -3.0e38f;
-                uint32_t pk[2][16];
-                {
-                    uint32_t v0[32], v1[32];
-                    auto process = [&](const uint32_t (&v)[32], int cc) {
-                        float y[32];
+                // ---- 4 chunks of 16 points: TMEM -> y = acc*es + b -> (ReLU) -> fp16 -> operand tile ----
+                // The load of chunk i+1 is in flight while chunk i is converted and stored.
+                const bool relu = f & JB_RELU;
+                const uint32_t row_addr = act + (ch >> 3) * kKGroup3 + pq * kNGroup3 + (ch & 7u) * 128u;
+                const uint32_t swz = (ch & 7u) << 4;
+                uint32_t va[16], vb[16];
+                auto process = [&](const uint32_t (&v)[16], int cc) {
+                    float y[16];
+                    uint32_t pk[8];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) y[i] = fmaxf(fmaf(__uint_as_float(v[i]), c.x, c.y), lo_clamp);
+                    for (int i = 0; i < 16; ++i) y[i] = fmaf(__uint_as_float(v[i]), c.x, c.y);
+                    if (relu) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) pk[cc][i] = pack_half2(y[2 * i], y[2 * i + 1]);
-                        if (f & JB_ALPHA) {
+                        for (int i = 0; i < 8; ++i) pk[i] = cvt_pack_f16_relu(y[2 * i], y[2 * i + 1]);
+                    } else {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) y[i] *= wa;
-                            const float s = column_reduce32_3(y, lane);
-                            atomicAdd(&out_s[pq * 64 + cc * 32 + lane], s);
-                        }
-                    };
-                    tmem_ld32(ta, v0);
-                    tmem_ld_wait();
-                    tmem_ld32(ta + 32, v1);
-                    process(v0, 0);
-                    tmem_ld_wait();
-                    process(v1, 1);
-                }
-                // ---- write the operand tile (channels of this half), after its last readers are done ----
-                if (f & JB_WAIT_SF) { mbar_wait(bar(kB3StageFree + (q >> 1)), ph_sf); ph_sf ^= 1; }
-                if (kSave) {
-                    if (lane == 0) bulk_wait_read_all();
-                    __syncwarp();
-                }
-                const uint32_t row_off = (ch >> 3) * kKGroup3 + pq * kNGroup3 + (ch & 7u) * 128u;
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint4 qv = make_uint4(pk[cc][4 * k], pk[cc][4 * k + 1], pk[cc][4 * k + 2], pk[cc][4 * k + 3]);
-                        *reinterpret_cast<uint4*>(act + row_off + ((((uint32_t)(cc * 4 + k)) ^ (ch & 7u)) << 4)) = qv;
+                        for (int i = 0; i < 8; ++i) pk[i] = cvt_pack_f16(y[2 * i], y[2 * i + 1]);
                     }
+                    if (cc == 0) {
+                        // first store of the job: the last readers of these channels must be done
+                        if (f & JB_WAIT_SF) {
+                            unsigned long long t1 = 0;
+                            if (tracing) t1 = clock64();
+                            mbar_wait(bar(kB3StageFree + (q >> 1)), ph_sf);
+                            ph_sf ^= 1;
+                            if (tracing) t_sf += clock64() - t1;
+                        }
+                        if (kSave) {
+                            if (lane == 0) bulk_wait_read_all();
+                            __syncwarp();
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        st_shared_v4(row_addr + ((uint32_t)((cc * 2 + k) << 4) ^ swz), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+                    if (f & JB_ALPHA) {        // L7 is a ReLU layer: the head sees max(y, 0)
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.0f) * wa;
+                        const float s = column_reduce16_3(y, lane);
+                        if (!(lane & 1)) red_shared_add_f32(out_sa + 4 * (pq * 64 + cc * 16 + (lane >> 1)), s);
+                    }
+                };
+                {
+                    tmem_ld16(ta, va);
+                    tmem_ld_wait();
+                    tmem_ld16(ta + 16, vb);
+                    process(va, 0);
+                    tmem_ld_wait();
+                    tmem_ld16(ta + 32, va);
+                    process(vb, 1);
+                    tmem_ld_wait();
+                    tmem_ld16(ta + 48, vb);
+                    process(va, 2);
+                    tmem_ld_wait();
+                    process(vb, 3);
                 }
+                if (tracing) { const unsigned long long dt = clock64() - t0; t_math += dt; if (j == j_sel) t_sel_math += dt; }
                 if (kSave) {
                     // this warp's 4 pieces of 1 KB (8 channels x 64 points each) -> HBM image of slot jb.slot
                     fence_proxy_async_smem();
@@ -196,14 +234,18 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                     }
                 }
                 if (f & JB_PE_AFTER) {          // the direction stage of this group has been accumulated
-                    const int next = g + stride;
-                    if (next < prm.n_groups) {
-                        load_point(next);
+                    if (g + stride < prm.n_groups) {
                         write_pe_half(enc, pt, role, p);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) vd[k] = vd_next[k];
                     }
                 }
                 publish(hi ? kB3ActHi : kB3ActLo);
+                if (tracing) { const unsigned long long dt = clock64() - t0; t_job += dt; if (j == j_sel) t_sel += dt; }
             }
+        }
+        if (tracing && prm.dbg) {
+            if (e == 5) { prm.dbg[8 * blockIdx.x + 4] = t_acc; prm.dbg[8 * blockIdx.x + 5] = t_sf; prm.dbg[8 * blockIdx.x + 6] = t_job; prm.dbg[8 * blockIdx.x + 7] = t_math; prm.dbg[8 * 148 + 32 * blockIdx.x] = t_sel; prm.dbg[8 * 148 + 32 * blockIdx.x + 1] = t_sel_math; }
         }
         if (kSave && lane == 0) bulk_wait_all();
     }
@@ -214,6 +256,12 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
 }
 
 }  // namespace nerfq
+
+static unsigned long long* g_trace3 = nullptr;
+static int g_trace3_flags = 0;
+// Profiling aid (not part of include/nerfq.h): when set, launches use the tracing instantiation of the kernels, which
+// writes 8 cycle counters per CTA into this device buffer (see profiles/trace_v3.py).
+extern "C" void nerfq_mlp3_set_trace(unsigned long long* buf, int flags) { g_trace3 = buf; g_trace3_flags = flags; }
 
 extern "C" int nerfq_mlp3_forward(const void* packed, const float* rays, const float* z, long long n_rays, int samples_per_ray,
                                   float* raw, void* save, int max_ctas, cudaStream_t stream) {
@@ -228,15 +276,14 @@ extern "C" int nerfq_mlp3_forward(const void* packed, const float* rays, const f
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
     const int grid = n_groups < sms ? n_groups : sms;
-    Fwd3Params prm{(const uint8_t*)packed, rays, z, raw, (uint8_t*)save, n_points, samples_per_ray, n_groups, prog};
-    if (save) {
-        if (cudaFuncSetAttribute(mlp3_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS3Bytes) != cudaSuccess) return -2;
-        mlp3_forward_kernel<true><<<grid, kThreads3, kS3Bytes, stream>>>(prm);
-    } else {
-        if (cudaFuncSetAttribute(mlp3_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS3Bytes) != cudaSuccess) return -2;
-        mlp3_forward_kernel<false><<<grid, kThreads3, kS3Bytes, stream>>>(prm);
-    }
-    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+    Fwd3Params prm{(const uint8_t*)packed, rays, z, raw, (uint8_t*)save, n_points, samples_per_ray, n_groups, g_trace3, g_trace3_flags, prog};
+    auto launch = [&](auto kernel) -> int {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kS3Bytes) != cudaSuccess) return -2;
+        kernel<<<grid, kThreads3, kS3Bytes, stream>>>(prm);
+        return cudaGetLastError() == cudaSuccess ? 0 : -3;
+    };
+    if (g_trace3) return save ? launch(mlp3_forward_kernel<true, true>) : launch(mlp3_forward_kernel<false, true>);
+    return save ? launch(mlp3_forward_kernel<true, false>) : launch(mlp3_forward_kernel<false, false>);
 }
 
 extern "C" unsigned long long nerfq_mlp3_save_bytes(long long n_points) {
