@@ -1,0 +1,372 @@
+// Fused NeRF MLP backward into the LSA scales on tcgen05 tensor cores (sm_100a), third generation.
+//
+// Replaces torch autograd over NeRF.forward with ScaledLinear layers (utils.py:57-80, transforms.py:104-111) when
+// only `weight_scaling` requires grad (framework/pytorch_model/__init__.py:1129-1145, run_nerf.py:756).  For a layer
+//   y = s * (delta * (L x)) + b        (L = integer levels, s = LSA scale per output channel)
+// the scale gradient is  ds[o] = sum_n dY[n,o] * (y[n,o] - b[o]) / s[o]  -- an elementwise product reduced over
+// points, no weight-gradient GEMM -- and the input gradient is the dgrad GEMM  dX = (dY * delta * s) L.
+//
+// Same CTA organisation as the forward kernel (mlp3_layout.h): per group of 256 points the chain of 9 dgrad GEMMs
+//   D[k][n] = sum_o L[o][k] * G[n][o]      (A = W^T chunks streamed from L2, B = gradient tile in shared memory)
+// runs with input channels k on the TMEM lanes, so an epilogue thread owns ONE channel of the layer whose output the
+// accumulator is the gradient of: it masks with the saved forward activation (ReLU), accumulates its channel's
+// scale-gradient sums in registers (no cross-lane reduction), and writes the next GEMM's operand row.  Saved
+// activations are read straight from the forward kernel's HBM images (L2-prefetched one job ahead).
+// Gradients are tiny (1e-7..1e-3): each group is multiplied by a power of two that brings max|d_raw| into [8,16)
+// -- backpropagation is linear, the factor is exact and is divided out where the scale-gradient sums are flushed --
+// which keeps fp16's 11-bit significand for the operands without its range problem.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "mlp3_common.cuh"
+
+namespace nerfq {
+
+struct Bwd3Params {
+    const uint8_t* packed;
+    const float* d_raw;      // [n_points, 4]
+    const float* raw;        // [n_points, 4]   forward output (for the rgb / alpha head terms)
+    const uint8_t* save;     // saved operand images from the forward pass (kSave3GroupBytes per group)
+    float* grad_tmp;         // [2436] scratch inside the packed buffer: sum_n dY (y - b) = s * ds, zero on entry
+    long long n_points;
+    int n_groups;
+    unsigned long long* dbg;     // tracing build only: 8 cycle counters per CTA
+    Prog3Bwd prog;
+};
+
+constexpr uint32_t kS3BwdGa = kS3BwdPg + 4096;          // float ga[256]: alpha-head gradient per point
+constexpr uint32_t kS3BwdMax = kS3BwdGa + 1024;         // uint gmax[2]
+static_assert(kS3BwdMax + 8 <= kS3Misc, "backward scratch must fit the encoding-tile region");
+
+// one 128-byte line into L2
+__device__ __forceinline__ void prefetch_l2_line(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p) : "memory");
+}
+// fire-and-forget float add into global memory (L2 atomic unit; a shared-memory float atomic is a compare-and-swap
+// loop on this architecture)
+__device__ __forceinline__ void red_global_add_f32(float* p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+// 32 bytes (16 saved activations of one channel) in one request; the L2 is asked to fetch the surrounding 256 bytes
+struct H32 { uint4 a, b; };
+__device__ __forceinline__ H32 ldg_nc_32B(const void* p) {
+    H32 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w) : "l"(p));
+    return r;
+}
+
+template <bool kTrace>
+__global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __grid_constant__ Bwd3Params prm) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = uniform_warp_idx();
+    const int lane = threadIdx.x & 31;
+    auto bar = [&](int i) { return sbase + kS3Bars + 8u * i; };
+
+    {
+        if (threadIdx.x < 2) reinterpret_cast<uint32_t*>(smem + kS3BwdMax)[threadIdx.x] = 0u;
+    }
+    const uint32_t tmem_base = setup3(smem, sbase, warp, kEpiWarps3 / 2);      // each half has its own team of 8 warps
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int n_iters = first < prm.n_groups ? (prm.n_groups - first + stride - 1) / stride : 0;
+
+    if (warp < kCtrlWarps3) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " NERFQ_REGS_CTRL3 ";");
+        if (warp == 0) {
+            loader3(sbase, prm.packed + kOffBwd3Image, kBwd3Chunks, n_iters);
+        } else if (warp == 1) {
+            if (n_iters > 0) issuer3<kBwd3Jobs, kTrace>(sbase, tmem_base, prm.prog.half, n_iters, false, prm.dbg);
+        }
+    } else {
+        // ================= epilogue warps =================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " NERFQ_REGS_EPI3 ";");
+        const int e = warp - kCtrlWarps3;
+        // Two teams of 8 warps: team 0 runs the jobs of channels 0..127 (and the views-layer job), team 1 those of
+        // channels 128..255, so the two jobs of a step overlap instead of queueing behind each other.  Within a team a
+        // warp owns lane quarter q and 128 points (ph).
+        const int q = warp & 3, team = e >> 3, ph = (e >> 2) & 1;
+        const uint32_t tmem_lane = tmem_base + (uint32_t(q * 32) << 16) + team * 256 + ph * 128;
+        const uint32_t act = sbase + kS3Act;
+        const uint32_t pg_a = sbase + kS3BwdPg, ga_a = sbase + kS3BwdGa, max_a = sbase + kS3BwdMax;
+        const float2* g_sb = reinterpret_cast<const float2*>(prm.packed + kOffSB);
+        const float* g_wa = reinterpret_cast<const float*>(prm.packed + kOffWAlpha);
+        const float* g_wr = reinterpret_cast<const float*>(prm.packed + kOffWRgb);
+        uint32_t ph_acc = 0, ph_sf = 0;
+        unsigned long long t_pro = 0, t_acc = 0, t_job = 0, t_views = 0;
+        const bool tracing = kTrace && lane == 0 && (e == 1 || e == 9);
+        const int cl = 32 * q + lane;                 // this thread's channel within a half (its TMEM lane)
+
+        auto publish = [&](int which) {
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(which));
+        };
+        // saved rows of this thread: 64 points of channel (chh) in image `slot` -> 8 x 16-byte pieces
+        auto saved_row = [&](int g, int slot, uint32_t chh) {
+            return prm.save + (size_t)g * kSave3GroupBytes + (size_t)slot * kAct3Bytes + (chh >> 3) * kKGroup3 + (2 * ph) * kNGroup3 +
+                   (chh & 7u) * 128u;
+        };
+        // one chunk of 16 points of this thread's channel.  d = gradient w.r.t. the layer output (fp32, from TMEM),
+        // h = saved activations (8 x half2).  The elementwise work runs on packed halves:
+        //   dh = fp16(d);  s1h += dh*h;  g = dh*es (masked where the unit was inactive);  s2h += g;  G row <- g
+        // The half2 partial sums cover 8 terms each and are folded into the fp32 sums per chunk (rounding errors are
+        // unbiased and average out over the ~10^5 chunks a channel sees).
+        auto chunk16 = [&](const float (&d)[16], const uint4 h0, const uint4 h1, __half2 es2, bool relu, bool write, uint32_t row_addr,
+                           uint32_t swz, int cc, float& s1, float& s2) {
+            const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            uint32_t pk[8];
+            const __half2 zero2 = __float2half2_rn(0.0f);
+            __half2 s1h = zero2, s2h = zero2;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const __half2 h2 = *reinterpret_cast<const __half2*>(&hw[i]);
+                const uint32_t dw = cvt_pack_f16(d[2 * i], d[2 * i + 1]);
+                const __half2 dh = *reinterpret_cast<const __half2*>(&dw);
+                s1h = __hfma2(dh, h2, s1h);
+                __half2 g2 = __hmul2(dh, es2);
+                if (relu) g2 = __hmul2(g2, __hgt2(h2, zero2));       // mask: 1.0 where the unit was active
+                s2h = __hadd2(s2h, g2);
+                pk[i] = *reinterpret_cast<const uint32_t*>(&g2);
+            }
+            const float2 a1 = __half22float2(s1h), a2 = __half22float2(s2h);
+            s1 += a1.x + a1.y;
+            s2 += a2.x + a2.y;
+            if (write) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    st_shared_v4(row_addr + (cc >> 2) * kNGroup3 + ((uint32_t)(((cc & 3) * 2 + k) << 4) ^ swz), pk[4 * k], pk[4 * k + 1],
+                                 pk[4 * k + 2], pk[4 * k + 3]);
+            }
+        };
+        // The 16 points of chunk cc (0..7) of this thread's row are two 16-byte pieces at swizzled positions 2c^x and
+        // (2c+1)^x (x = channel & 7): one aligned 32-byte pair, in swapped order when x is odd.
+        auto pair_off = [&](int cc, uint32_t swz) { return (uint32_t)((cc >> 2) * kNGroup3) + (((uint32_t)((cc & 3) << 5)) ^ (swz & 0x60u)); };
+        // 64 KB slice of saved activations read by this team's i-th job of group g.  Team 0: views job (i = 0), then
+        // jobs 0, 2, .., 16; team 1: jobs 1, 3, .., 17.  i past the end continues in the CTA's next group.
+        const int team_jobs = team == 0 ? kBwd3Jobs / 2 + 1 : kBwd3Jobs / 2;
+        auto slice_ptr = [&](int g, int i) -> const uint8_t* {
+            if (i >= team_jobs) { i -= team_jobs; g += stride; }
+            if (g >= prm.n_groups) g = prm.n_groups - 1;
+            const uint8_t* base = prm.save + (size_t)g * kSave3GroupBytes;
+            if (team == 0 && i == 0) return base + (size_t)9 * kAct3Bytes;
+            const Job3 jn = prm.prog.job[team == 0 ? 2 * (i - 1) : 2 * i + 1];
+            return base + (size_t)jn.slot * kAct3Bytes + ((jn.flags & JB_HI_HALF) ? kAct3Bytes / 2 : 0);
+        };
+        const int tl = (e & 7) * 32 + lane;        // thread index within the team: prefetches lines tl and tl + 256
+        auto prefetch_slice = [&](const uint8_t* sl) {
+            prefetch_l2_line(sl + 128 * tl);
+            prefetch_l2_line(sl + 128 * (tl + 256));
+        };
+        float2 c_next = make_float2(1.f, 0.f);
+        if (n_iters > 0) {
+            if (team == 1) publish(kB3ActHi);       // D_hi is free at kernel start
+            c_next = __ldg(&g_sb[prm.prog.job[team].ch + cl]);
+        }
+        int it = 0;
+        for (int g = first; g < prm.n_groups; g += stride, ++it) {
+            // ================= prologue: head gradients, group scale, views-layer gradient =================
+            unsigned long long tp0 = 0;
+            if (tracing) tp0 = clock64();
+            const int pt = e * 32 + lane;             // warps 0..7 own one point each
+            const long long gidx = (long long)g * kGroupPts + pt;
+            float4 dr = make_float4(0.f, 0.f, 0.f, 0.f), rw = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < 8 && gidx < prm.n_points) {
+                dr = *reinterpret_cast<const float4*>(prm.d_raw + 4 * gidx);
+                rw = *reinterpret_cast<const float4*>(prm.raw + 4 * gidx);
+            }
+            if (it == 0) {         // later groups: prefetched by the previous group's last jobs
+                prefetch_slice(slice_ptr(g, 0));
+                prefetch_slice(slice_ptr(g, 1));
+            }
+            const uint32_t slot_max = max_a + 4 * (it & 1);
+            if (e < 8) {
+                float m = fmaxf(fmaxf(fabsf(dr.x), fabsf(dr.y)), fmaxf(fabsf(dr.z), fabsf(dr.w)));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (lane == 0) asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(slot_max), "r"(__float_as_uint(m)) : "memory");
+                // head scale gradients (unscaled): sum_n dr * (raw - b)
+                float pr = dr.x * (rw.x - __ldg(&g_sb[kChRgb + 0]).y);
+                float pgn = dr.y * (rw.y - __ldg(&g_sb[kChRgb + 1]).y);
+                float pb = dr.z * (rw.z - __ldg(&g_sb[kChRgb + 2]).y);
+                float pa = dr.w * (rw.w - __ldg(&g_sb[kChAlpha]).y);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    pr += __shfl_xor_sync(0xffffffffu, pr, o);
+                    pgn += __shfl_xor_sync(0xffffffffu, pgn, o);
+                    pb += __shfl_xor_sync(0xffffffffu, pb, o);
+                    pa += __shfl_xor_sync(0xffffffffu, pa, o);
+                }
+                if (lane == 0) {
+                    red_global_add_f32(prm.grad_tmp + kChRgb + 0, pr);
+                    red_global_add_f32(prm.grad_tmp + kChRgb + 1, pgn);
+                    red_global_add_f32(prm.grad_tmp + kChRgb + 2, pb);
+                    red_global_add_f32(prm.grad_tmp + kChAlpha, pa);
+                }
+            }
+            named_bar_sync3(1, 32 * kEpiWarps3);
+            float rscale = 0.0f, rinv = 0.0f;
+            {
+                uint32_t mbits;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mbits) : "r"(slot_max) : "memory");
+                const int ex = (mbits >> 23) & 0xff;
+                if (ex >= 16 && ex <= 240) {
+                    rscale = __int_as_float((257 - ex) << 23);       // max|d_raw| * rscale in [8, 16)
+                    rinv = __int_as_float((ex - 3) << 23);
+                }
+            }
+            if (e < 8) {
+                const float er = __ldg(&g_sb[kChRgb + 0]).x, eg = __ldg(&g_sb[kChRgb + 1]).x, eb = __ldg(&g_sb[kChRgb + 2]).x;
+                const float ea = __ldg(&g_sb[kChAlpha]).x;
+                st_shared_v4(pg_a + 16 * pt, __float_as_uint(dr.x * rscale * er), __float_as_uint(dr.y * rscale * eg),
+                             __float_as_uint(dr.z * rscale * eb), 0u);
+                st_shared_f32(ga_a + 4 * pt, dr.w * rscale * ea);
+            }
+            if (e == 8 && lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(max_a + 4 * ((it & 1) ^ 1)), "r"(0u) : "memory");
+            named_bar_sync3(1, 32 * kEpiWarps3);
+
+            // ---- views-layer job (team 0): d hv[k][n] = sum_c g_c[n] * w_rgb[c][k], channels 0..127 ----
+            if (tracing) { const unsigned long long t = clock64(); t_pro += t - tp0; tp0 = t; }
+            if (team == 0) {
+                const uint32_t chh = cl;                                   // views hidden channel
+                const float2 c = __ldg(&g_sb[kChViews + chh]);
+                const float w0 = __ldg(&g_wr[chh]), w1 = __ldg(&g_wr[128 + chh]), w2 = __ldg(&g_wr[256 + chh]);
+                const uint8_t* hrow = saved_row(g, 9, chh);
+                const uint32_t row_addr = act + (chh >> 3) * kKGroup3 + (2 * ph) * kNGroup3 + (chh & 7u) * 128u;
+                const uint32_t swz = (chh & 7u) << 4;
+                prefetch_slice(slice_ptr(g, 2));
+                const bool odd = chh & 1u;
+                float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll 1
+                for (int cc = 0; cc < 8; ++cc) {
+                    const H32 hp = ldg_nc_32B(hrow + pair_off(cc, swz));
+                    float d[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float4 gq = ld_shared_v4f(pg_a + 16 * (ph * 128 + cc * 16 + i));
+                        d[i] = fmaf(gq.x, w0, fmaf(gq.y, w1, gq.z * w2));
+                    }
+                    chunk16(d, odd ? hp.b : hp.a, odd ? hp.a : hp.b, __float2half2_rn(c.x), true, true, row_addr, swz, cc, s1, s2);
+                }
+                // ds * s = sum dY (y - b) = s1 - b * (sum dY);  s2 accumulated dY*es
+                publish(kB3ActLo);
+                red_global_add_f32(prm.grad_tmp + kChViews + chh, (s1 - c.y * (s2 / c.x)) * rinv);
+            }
+
+            // ================= dgrad chain: this team's jobs =================
+            if (tracing) t_views += clock64() - tp0;
+#pragma unroll 1
+            for (int j = team; j < kBwd3Jobs; j += 2) {
+                const Job3 jb = prm.prog.job[j];
+                const uint32_t f = jb.flags;
+                const uint32_t chh = 128u * team + cl;                     // channel within the layer
+                const float2 c = c_next;
+                const float wa = (f & JB_ADD_ALPHA) ? __ldg(&g_wa[chh]) : 0.0f;
+                const uint8_t* hrow = saved_row(g, jb.slot, chh);
+                const uint32_t row_addr = act + (chh >> 3) * kKGroup3 + (2 * ph) * kNGroup3 + (chh & 7u) * 128u;
+                const uint32_t swz = (chh & 7u) << 4;
+                // saved activations: two chunks are requested before the accumulator is waited for, then each consumed
+                // slot is refilled with the chunk two ahead
+                const bool odd = chh & 1u;
+                H32 hh[2];
+                hh[0] = ldg_nc_32B(hrow + pair_off(0, swz));
+                hh[1] = ldg_nc_32B(hrow + pair_off(1, swz));
+                // L2 prefetch of the slice this team needs two jobs from now (512 lines, two per thread)
+                prefetch_slice(slice_ptr(g, (team == 0 ? j / 2 + 1 : j / 2) + 2));
+                unsigned long long tj0 = 0;
+                if (tracing) tj0 = clock64();
+                mbar_wait(bar(kB3AccReady + team), ph_acc);
+                ph_acc ^= 1;
+                tc_fence_after_sync();
+                if (tracing) { const unsigned long long t = clock64(); t_acc += t - tj0; tj0 = t; }
+                c_next = __ldg(&g_sb[prm.prog.job[j + 2 < kBwd3Jobs ? j + 2 : team].ch + cl]);        // in flight during this job
+                const bool relu = f & JB_RELU, write = !(f & JB_NO_WRITE);
+                const __half2 es2 = __float2half2_rn(c.x);
+                float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    uint32_t va[16];
+                    tmem_ld16(tmem_lane + 16 * cc, va);
+                    tmem_ld_wait();
+                    float d[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) d[i] = __uint_as_float(va[i]);
+                    if (f & JB_ADD_ALPHA) {        // d h8 also receives the alpha head's gradient
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 ga = ld_shared_v4f(ga_a + 4 * (ph * 128 + cc * 16 + i));
+                            d[i] = fmaf(ga.x, wa, d[i]);
+                            d[i + 1] = fmaf(ga.y, wa, d[i + 1]);
+                            d[i + 2] = fmaf(ga.z, wa, d[i + 2]);
+                            d[i + 3] = fmaf(ga.w, wa, d[i + 3]);
+                        }
+                    }
+                    if (cc == 0 && (f & JB_WAIT_SF)) { mbar_wait(bar(kB3StageFree + (q >> 1)), ph_sf); ph_sf ^= 1; }
+                    const H32 hp = hh[cc & 1];
+                    if (cc < 6) hh[cc & 1] = ldg_nc_32B(hrow + pair_off(cc + 2, swz));       // refill with chunk cc + 2
+                    chunk16(d, odd ? hp.b : hp.a, odd ? hp.a : hp.b, es2, relu, write, row_addr, swz, cc, s1, s2);
+                }
+                if (write || team) publish(team ? kB3ActHi : kB3ActLo);
+                red_global_add_f32(prm.grad_tmp + jb.ch + cl, (s1 - c.y * (s2 / c.x)) * rinv);     // after the hand-over
+                if (tracing) t_job += clock64() - tj0;
+            }
+        }
+        if (tracing && prm.dbg) {
+            unsigned long long* o = prm.dbg + 8 * 148 + 32 * blockIdx.x + 8 * team;
+            o[0] = t_pro; o[1] = t_views; o[2] = t_acc; o[3] = t_job;
+        }
+    }
+
+    // ---- teardown ----
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// d_scale[i] += tmp[i] / s[i];  tmp[i] = 0  (the scratch is left zeroed for the next launch)
+__global__ void mlp3_backward_finalize_kernel(uint8_t* packed, float* __restrict__ d_scale) {
+    float* tmp = reinterpret_cast<float*>(packed + kOffGradTmp3);
+    const float* scale = reinterpret_cast<const float*>(packed + kOffScale);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < kNumChannels) {
+        const float v = tmp[i];
+        tmp[i] = 0.0f;
+        if (v != 0.0f) d_scale[i] += v / scale[i];
+    }
+}
+
+}  // namespace nerfq
+
+static unsigned long long* g_trace3b = nullptr;
+// Profiling aid (not part of include/nerfq.h): see nerfq_mlp3_set_trace.
+extern "C" void nerfq_mlp3_set_trace_bwd(unsigned long long* buf) { g_trace3b = buf; }
+
+extern "C" int nerfq_mlp3_backward(const void* packed, const float* d_raw, const float* raw, const void* save, long long n_points,
+                                   float* d_scale, int max_ctas, cudaStream_t stream) {
+    using namespace nerfq;
+    if (n_points == 0) return 0;
+    if (!packed || !d_raw || !raw || !save || !d_scale || n_points < 0) return -1;
+    static const Prog3Bwd prog = make_prog3_bwd();
+    const int n_groups = (int)((n_points + kGroupPts - 1) / kGroupPts);
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
+    const int grid = n_groups < sms ? n_groups : sms;
+    // the kernel accumulates s*ds into a scratch array of the packed buffer (zeroed by nerfq_pack_net and by every
+    // finalize), the finalize kernel divides by the LSA scale and adds into d_scale
+    uint8_t* pk = (uint8_t*)const_cast<void*>(packed);
+    Bwd3Params prm{(const uint8_t*)packed, d_raw, raw, (const uint8_t*)save, reinterpret_cast<float*>(pk + kOffGradTmp3), n_points, n_groups,
+                   g_trace3b, prog};
+    if (g_trace3b) {
+        if (cudaFuncSetAttribute(mlp3_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS3Bytes) != cudaSuccess) return -2;
+        mlp3_backward_kernel<true><<<grid, kThreads3, kS3Bytes, stream>>>(prm);
+    } else {
+        if (cudaFuncSetAttribute(mlp3_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS3Bytes) != cudaSuccess) return -2;
+        mlp3_backward_kernel<false><<<grid, kThreads3, kS3Bytes, stream>>>(prm);
+    }
+    mlp3_backward_finalize_kernel<<<(kNumChannels + 255) / 256, 256, 0, stream>>>(pk, d_scale);
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}

@@ -6,9 +6,14 @@
 
 namespace nerfq {
 
-// warp 0: weight loader   warp 1: MMA issuer   warp 2: TMEM owner   warp 3: spare
-// warps 4..19: epilogue; warp e = warp - 4 owns TMEM lanes 32*(e & 3).. and points 64*(e >> 2)..
+// warp 0: weight loader (and TMEM owner)   warp 1: MMA issuer   warps 2, 3: idle (they complete the control warp group)
+// warps 4..19: epilogue; a warp may only touch TMEM lanes 32*(warp % 4).., so warp w owns lane quarter q = w & 3 and
+// point quarter pq = (w - 4) >> 2.
+// Registers: 20 warps are launched with 96 registers each; the control warp group then releases registers
+// (setmaxnreg.dec) and the four epilogue warp groups claim them (setmaxnreg.inc) -- see kRegsCtrl3 / kRegsEpi3.
 constexpr int kCtrlWarps3 = 4;
+#define NERFQ_REGS_CTRL3 "56"
+#define NERFQ_REGS_EPI3 "104"
 constexpr int kEpiWarps3 = 16;
 constexpr int kThreads3 = 32 * (kCtrlWarps3 + kEpiWarps3);
 constexpr int kSlots3 = 4;
@@ -49,19 +54,19 @@ __device__ __forceinline__ void named_bar_sync3(int id, int nthreads) {
 }
 
 // ---- one-time setup shared by both kernels; returns the TMEM base -----------------------------------
-__device__ __forceinline__ uint32_t setup3(uint8_t* smem, uint32_t sbase, int warp) {
+__device__ __forceinline__ uint32_t setup3(uint8_t* smem, uint32_t sbase, int warp, int act_arrivals = kEpiWarps3) {
     auto bar = [&](int i) { return sbase + kS3Bars + 8u * i; };
     if (threadIdx.x == 0) {
         for (int i = 0; i < kSlots3; ++i) { mbar_init(bar(kB3WFull + i), 1); mbar_init(bar(kB3WEmpty + i), 1); }
-        mbar_init(bar(kB3ActLo), kEpiWarps3);
-        mbar_init(bar(kB3ActHi), kEpiWarps3);
+        mbar_init(bar(kB3ActLo), act_arrivals);
+        mbar_init(bar(kB3ActHi), act_arrivals);
         mbar_init(bar(kB3AccReady + 0), 1);
         mbar_init(bar(kB3AccReady + 1), 1);
         mbar_init(bar(kB3StageFree + 0), 1);
         mbar_init(bar(kB3StageFree + 1), 1);
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc(sbase + kS3TmemPtr, 512);
+    if (warp == 0) tmem_alloc(sbase + kS3TmemPtr, 512);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
     } else if (warp >= kCtrlWarps3) {
         // ================= epilogue warps =================
         const int e = warp - kCtrlWarps3;
-        const int q = e & 3, pq = e >> 2;
+        const int q = warp & 3, pq = e >> 2;
         const uint32_t tmem_lane = tmem_base + (uint32_t(q * 32) << 16) + pq * 64;
         const uint32_t act = sbase + kS3Act;      // shared-space addresses
         const uint32_t enc = sbase + kS3Enc;
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace nerfq

@@ -230,7 +230,8 @@ inline Prog3Bwd make_prog3_bwd() {
 // ---- packed network buffer: v3 images appended after the first-generation fields -----------------
 constexpr size_t kOffFwd3Image = (kPackedBytes + 1023) / 1024 * 1024;
 constexpr size_t kOffBwd3Image = kOffFwd3Image + kFwd3ImageBytes;
-constexpr size_t kPacked3Bytes = kOffBwd3Image + kBwd3ImageBytes;
+constexpr size_t kOffGradTmp3 = kOffBwd3Image + kBwd3ImageBytes;          // float[2440] backward scratch (kept zeroed)
+constexpr size_t kPacked3Bytes = kOffGradTmp3 + 4 * 2440;
 
 // ---- saved activations: per group 9 MN-major images of 128 KB (h1..h8, feature) + 64 KB (views hidden) ----
 constexpr size_t kSave3GroupBytes = 9 * (size_t)kAct3Bytes + kAct3Bytes / 2;

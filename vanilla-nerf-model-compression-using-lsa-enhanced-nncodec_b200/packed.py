@@ -76,7 +76,7 @@ class PackedNet:
         return self.buf.data_ptr()
 
 
-IMPL = {"version": 1}      # 3: channels-on-lanes kernels (mlp3_*.cu); 1: first-generation kernels (mlp_*.cu)
+IMPL = {"version": int(__import__("os").environ.get("NERFQ_MLP_IMPL", "1"))}      # 3: channels-on-lanes kernels (mlp3_*.cu); 1: first-generation kernels (mlp_*.cu)
 
 
 def mlp_save_bytes(n_points: int, impl: Optional[int] = None) -> int:
