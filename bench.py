@@ -179,7 +179,6 @@ def run_cuda(args):
     opt = torch.optim.Adam(params, lr=1e-4)
     train_kw, _ = R.create_nerf(wrapper, perturb=1.0, white_bkgd=True, dataset_type="blender")
     R.DATA_PARALLEL["enabled"] = world > 1
-    R.TUNING["pingpong"] = not args.no_pingpong
 
     o_h, d_h, t_h = synth_batch(RAYS_PER_GPU, 2 + 10 * rank)
     rays_h = torch.stack([o_h, d_h], 0).pin_memory()          # [2, N, 3] as run_nerf.py:739 passes `batch_rays`
@@ -265,14 +264,14 @@ def run_cuda(args):
         for name, S in (("coarse", N_SAMPLES), ("fine", N_SAMPLES + N_IMPORTANCE)):
             z = torch.sort(2.0 + 4.0 * torch.rand(RAYS_PER_GPU, S, device=dev), -1).values.contiguous()
             save = torch.empty(packed.mlp_save_bytes(RAYS_PER_GPU * S), dtype=torch.uint8, device=dev)
-            raw = packed.mlp_forward(pn, rays11, z, save=save, pingpong=R.TUNING["pingpong"])
+            raw = packed.mlp_forward(pn, rays11, z, save=save)
             d_raw = torch.randn_like(raw) * 1e-5
             acc = torch.zeros(2436, device=dev)
-            kern[f"mlp_fwd_{name}"] = (timed(lambda: packed.mlp_forward(pn, rays11, z, save=save, pingpong=R.TUNING["pingpong"]), 10, 3)
+            kern[f"mlp_fwd_{name}"] = (timed(lambda: packed.mlp_forward(pn, rays11, z, save=save), 10, 3)
                                        if world == 1 else None, RAYS_PER_GPU * S * FLOP_PER_POINT_FWD)
             kern[f"mlp_bwd_{name}"] = (timed(lambda: ops.mlp_backward(pn, d_raw, raw, save, acc), 10, 3) if world == 1 else None,
                                        RAYS_PER_GPU * S * FLOP_PER_POINT_BWD)
-            kern[f"mlp_fwd_nosave_{name}"] = (timed(lambda: packed.mlp_forward(pn, rays11, z, pingpong=R.TUNING["pingpong"]), 10, 3)
+            kern[f"mlp_fwd_nosave_{name}"] = (timed(lambda: packed.mlp_forward(pn, rays11, z), 10, 3)
                                               if world == 1 else None, RAYS_PER_GPU * S * FLOP_PER_POINT_FWD)
             del save
 
@@ -289,7 +288,7 @@ def run_cuda(args):
                                        "render 4096 rays/GPU, 64+128 samples -> backward into LSA scales -> Adam)",
                            "rays_per_gpu": RAYS_PER_GPU, "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE, "qp": QP,
                            "perturb": 1.0, "white_bkgd": True, "requantize_every_step": requant_each_step,
-                           "operands": "fp16 operands, fp32 accumulate (TMEM)", "pingpong": R.TUNING["pingpong"],
+                           "operands": "fp16 operands, fp32 accumulate (TMEM)",
                            "parallelism": f"dp{world}" if world > 1 else "single",
                            "l2": "per-step working set (saved activations 5.1 GB/GPU) exceeds the 126 MB L2; no explicit flush"},
                 "e2e": {"value": world * RAYS_PER_GPU / (ms_e2e * 1e-3), "unit": "rays/s",
@@ -329,7 +328,6 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-requant", action="store_true", help="quantise once before the loop (what the reference does)")
-    ap.add_argument("--no-pingpong", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -61,18 +61,21 @@ int nerfq_set_scale_bias(void* packed, const float* scale, const float* bias, ne
  * Fused positional encoding + MLP (replaces run_network + NeRF.forward)
  *   framework/nerf_model/run_nerf.py:46-63,408,430; run_nerf_helpers.py:18-67; utils.py:57-80
  * rays [n_rays,11] = o(3) d(3) near far viewdir(3); z [n_rays,S]; raw [n_rays,S,4] = rgb logits, sigma.
+ * The sample points o + d*z, their positional encodings and all layer activations stay on chip; operands are fp16
+ * (weights: exact integer levels), accumulation is fp32, the epilogue applies delta*scale and bias in fp32.
  * save (nullable): nerfq_mlp_save_bytes(n_rays*S) bytes receiving the activations the backward needs.
- * pingpong: 0 = the two tiles of a CTA share every weight stage, 1 = they alternate (epilogue/MMA overlap).
  * max_ctas: 0 = one CTA per SM.
  * ---------------------------------------------------------------------------------------------- */
 int nerfq_mlp_forward(const void* packed, const float* rays, const float* z, long long n_rays, int samples_per_ray,
-                      float* raw, void* save, int pingpong, int max_ctas, nerfq_stream_t stream);
+                      float* raw, void* save, int max_ctas, nerfq_stream_t stream);
 unsigned long long nerfq_mlp_save_bytes(long long n_points);
 
 /* Gradient of the loss w.r.t. the LSA scales (replaces torch autograd over NeRF.forward with only
  * weight_scaling trainable: framework/pytorch_model/__init__.py:1129-1145, run_nerf.py:756).
- * d_scale [2436] is ACCUMULATED (caller zeroes). */
-int nerfq_mlp_backward(const void* packed, const float* d_raw, const float* raw, const void* save, long long n_points,
+ * d_scale [2436] is ACCUMULATED (caller zeroes).  `packed` is not const: a 10 KB scratch area inside it holds the
+ * partial sums of the launch (left zeroed again on completion), so one packed network must not run two backward
+ * launches concurrently. */
+int nerfq_mlp_backward(void* packed, const float* d_raw, const float* raw, const void* save, long long n_points,
                        float* d_scale, int max_ctas, nerfq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -4,7 +4,6 @@ import sys
 
 import torch
 
-os.environ["NERFQ_MLP_IMPL"] = "3"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import nerfq_b200  # noqa
 from nerfq_b200 import codec, model as nmodel, ops, packed
@@ -41,13 +40,13 @@ import ctypes
 import numpy as np
 from nerfq_b200 import _lib
 L = _lib.lib()
-L.nerfq_mlp3_set_trace_bwd.argtypes = [ctypes.c_void_p]
-L.nerfq_mlp3_set_trace_bwd.restype = None
+L.nerfq_mlp_set_trace_bwd.argtypes = [ctypes.c_void_p]
+L.nerfq_mlp_set_trace_bwd.restype = None
 buf = torch.zeros(148 * 8 + 148 * 32, dtype=torch.int64, device=dev)
-L.nerfq_mlp3_set_trace_bwd(buf.data_ptr())
+L.nerfq_mlp_set_trace_bwd(buf.data_ptr())
 ops.mlp_backward(pn, d_raw, raw, save, acc)
 torch.cuda.synchronize()
-L.nerfq_mlp3_set_trace_bwd(None)
+L.nerfq_mlp_set_trace_bwd(None)
 groups = (n * S // 256 + 147) // 148
 t = buf.cpu().numpy()[:148 * 8].reshape(148, 8).astype(np.float64).mean(0) / groups
 w = buf.cpu().numpy()[148 * 8:].reshape(148, 32).astype(np.float64).mean(0) / groups

@@ -24,20 +24,20 @@ d = -d / d.norm(dim=-1, keepdim=True)
 rays = ops.pack_rays(o.to(dev), d.to(dev), False, 4, 4, 1.0, 2.0, 6.0)
 z = torch.sort(2.0 + 4.0 * torch.rand(n, S, device=dev), -1).values.contiguous()
 L = _lib.lib()
-L.nerfq_mlp3_set_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
-L.nerfq_mlp3_set_trace.restype = None
+L.nerfq_mlp_set_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
+L.nerfq_mlp_set_trace.restype = None
 buf = torch.zeros(148 * 8 + 148 * 32, dtype=torch.int64, device=dev)
-save = torch.empty(packed.mlp_save_bytes(n * S, impl=3), dtype=torch.uint8, device=dev)
+save = torch.empty(packed.mlp_save_bytes(n * S), dtype=torch.uint8, device=dev)
 for mode, kw, flags in ([("nosave", {}, 0), ("save", {"save": save}, 0)] +
                         [(f"nosave, job {j} timed", {}, j << 8) for j in (0, 1, 2, 3, 8, 9, 14, 15, 18, 19)] +
                         [(f"nosave, none of the three, job {j} timed", {}, 7 | (j << 8)) for j in (2, 3)]):
     for _ in range(2):
-        packed.mlp_forward(pn, rays, z, impl=3, **kw)
-    L.nerfq_mlp3_set_trace(buf.data_ptr(), flags)
+        packed.mlp_forward(pn, rays, z, **kw)
+    L.nerfq_mlp_set_trace(buf.data_ptr(), flags)
     buf.zero_()
-    packed.mlp_forward(pn, rays, z, impl=3, **kw)
+    packed.mlp_forward(pn, rays, z, **kw)
     torch.cuda.synchronize()
-    L.nerfq_mlp3_set_trace(None, 0)
+    L.nerfq_mlp_set_trace(None, 0)
     t = buf.cpu().numpy()[:148 * 8].reshape(148, 8).astype(np.float64)
     groups = (n * S // 256 + 147) // 148
     w = buf.cpu().numpy()[148 * 8:].reshape(148, 32).astype(np.float64).mean(0) / groups

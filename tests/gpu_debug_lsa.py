@@ -46,8 +46,7 @@ def main():
     target = torch.rand(n, 3, device=dev)
     params = [q for q in w.parameters() if q.requires_grad]
     opt = torch.optim.Adam(params, lr=1e-4)
-    for pp in (True, False):
-        R.TUNING["pingpong"] = pp
+    for pp in (0,):
         for it in range(3):
             out = R.render_rays(batch, **kw)
             loss = R.img2mse(out["rgb_map"], target) + R.img2mse(out["rgb0"], target)
@@ -67,14 +66,14 @@ def main():
             e[3].record()
             torch.cuda.synchronize()
             tf += e[0].elapsed_time(e[1]); tb += e[1].elapsed_time(e[2])
-        print(f"LSA step 4096 rays pingpong={pp}: fwd {tf / iters:.3f} ms  bwd {tb / iters:.3f} ms  -> {1000.0 / ((tf + tb) / iters):.1f} steps/s (excl. Adam)")
+        print(f"LSA step 4096 rays: fwd {tf / iters:.3f} ms  bwd {tb / iters:.3f} ms  -> {1000.0 / ((tf + tb) / iters):.1f} steps/s (excl. Adam)")
     # kernel-level timing of the two MLP passes
     pn = w.model_fine.packed_net()
     z = torch.sort(2.0 + 4.0 * torch.rand(n, 192, device=dev), -1).values.contiguous()
     save = torch.empty(packed.mlp_save_bytes(n * 192), dtype=torch.uint8, device=dev)
-    for pp in (True, False):
-        for name, fn in (("fwd nosave", lambda: packed.mlp_forward(pn, batch, z, pingpong=pp)),
-                         ("fwd save", lambda: packed.mlp_forward(pn, batch, z, save=save, pingpong=pp))):
+    for pp in (0,):
+        for name, fn in (("fwd nosave", lambda: packed.mlp_forward(pn, batch, z)),
+                         ("fwd save", lambda: packed.mlp_forward(pn, batch, z, save=save))):
             fn(); torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -82,8 +81,8 @@ def main():
                 fn()
             b.record(); torch.cuda.synchronize()
             ms = a.elapsed_time(b) / 5
-            print(f"  {name} pingpong={pp}: {ms:.3f} ms  {n * 192 * 1.186816e6 / ms / 1e9:.0f} TFLOP/s")
-    raw = packed.mlp_forward(pn, batch, z, save=save, pingpong=True)
+            print(f"  {name}: {ms:.3f} ms  {n * 192 * 1.186816e6 / ms / 1e9:.0f} TFLOP/s")
+    raw = packed.mlp_forward(pn, batch, z, save=save)
     d_raw = torch.randn_like(raw) * 1e-5
     ops.mlp_backward(pn, d_raw, raw, save); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -1,7 +1,8 @@
-"""GPU-box debug script (not a pytest): run the fused MLP forward on the golden model, decode the
-saved operand tiles and print per-layer errors against the oracle."""
-import sys
+"""GPU-box debug script for the fused MLP forward kernel: per-layer errors from the saved
+MN-major operand images, raw output error, timing."""
 import os
+import sys
+
 import numpy as np
 import torch
 
@@ -11,24 +12,6 @@ import nerfq_b200  # noqa
 from nerfq_b200 import packed
 from oracle import render_oracle as ro
 from tests.util import golden_model_params, golden_model_levels, synth_rays, LAYERS
-
-SAVE_TILE = 9 * 65536 + 32768
-
-
-def decode_block_index():
-    r = np.arange(128)[:, None]
-    k = np.arange(64)[None, :]
-    return (r * 128 + (((k // 8) ^ (r & 7)) * 16) + (k % 8) * 2) // 2      # uint16 index within a 16 KB block
-
-
-def decode_tile(buf_u16, tile, slot, width):
-    idx = decode_block_index()
-    base = (tile * SAVE_TILE + slot * 65536) // 2
-    cols = []
-    for b in range(width // 64):
-        blk = buf_u16[base + b * 8192: base + (b + 1) * 8192]
-        cols.append(blk[idx])
-    return np.concatenate(cols, axis=1).view(np.float16).astype(np.float32)
 
 
 def oracle_intermediates(p, net, pts, vd):
@@ -56,60 +39,67 @@ def build_net(net, dev):
     ss = [p[f"{net}.{l}.weight_scaling"].to(dev) for l in LAYERS]
     return packed.PackedNet(ws, [delta] * 12, bs, ss), p
 
+ACT = 131072
+GROUP_BYTES = 9 * ACT + ACT // 2
+
+
+def decode_image(buf_u8, group, slot, width):
+    """MN-major activation image -> [256 points, width channels] float32."""
+    k = np.arange(width)[None, :]
+    n = np.arange(256)[:, None]
+    off = (k >> 3) * 4096 + (n >> 6) * 1024 + (k & 7) * 128 + ((((n & 63) >> 3) ^ (k & 7)) << 4) + (n & 7) * 2
+    base = group * GROUP_BYTES + slot * ACT
+    u16 = buf_u8[base: base + ACT].view(np.uint16)
+    return u16[off // 2].view(np.float16).astype(np.float32)
+
 
 def main():
     dev = torch.device("cuda:0")
-    net_name = "model"
-    pn, p = build_net(net_name, dev)
-    n_rays, S = 300, 64
+    pn, p = build_net("model", dev)
+    n_rays, S = 301, 64
     rays = synth_rays(n_rays, 11)
     z = ro.coarse_depths(rays[:, 6:7], rays[:, 7:8], S).contiguous()
-    for pingpong in (False, True):
-        save = torch.zeros(packed.mlp_save_bytes(n_rays * S), dtype=torch.uint8, device=dev)
-        raw = packed.mlp_forward(pn, rays.to(dev), z.to(dev), save=save, pingpong=pingpong)
-        torch.cuda.synchronize()
-        raw = raw.cpu().reshape(-1, 4)
-        pts = (rays[:, None, 0:3] + rays[:, None, 3:6] * z[:, :, None]).reshape(-1, 3)
-        vd = rays[:, None, 8:11].expand(n_rays, S, 3).reshape(-1, 3)
-        with torch.no_grad():
-            hs, feat, hv, raw_ref = oracle_intermediates(p, net_name, pts, vd)
-        buf = save.cpu().numpy().view(np.uint16)
-        M = n_rays * S
-        ntiles = (M + 127) // 128
-        print(f"--- pingpong={pingpong}  points={M} tiles={ntiles}")
-        names = ["h1", "h2", "h3", "h4", "h5", "h6", "h7", "h8", "feat"]
-        refs = hs + [feat]
-        for slot, (nm, ref) in enumerate(zip(names, refs)):
-            got = np.concatenate([decode_tile(buf, t, slot, 256) for t in range(ntiles)], 0)[:M]
-            err = np.abs(got - ref.numpy())
-            print(f"  {nm}: max|ref|={np.abs(ref.numpy()).max():.4f} maxerr={err.max():.5f} meanerr={err.mean():.6f}")
-        got = np.concatenate([decode_tile(buf, t, 9, 128) for t in range(ntiles)], 0)[:M]
-        err = np.abs(got - hv.numpy())
-        print(f"  hv: max|ref|={np.abs(hv.numpy()).max():.4f} maxerr={err.max():.5f}")
-        err = (raw - raw_ref).abs()
-        print(f"  raw: max|ref|={raw_ref.abs().max():.4f} maxerr={err.max():.5f} per-channel {err.max(0).values.tolist()}")
-        print("  raw sample", raw[:2].tolist(), raw_ref[:2].tolist())
-        # no-save run must give identical raw
-        raw2 = packed.mlp_forward(pn, rays.to(dev), z.to(dev), pingpong=pingpong).cpu().reshape(-1, 4)
-        print("  save vs nosave identical:", bool((raw2 == raw).all()), " finite:", bool(torch.isfinite(raw).all()))
-    # timing at a larger size
+    M = n_rays * S
+    save = torch.zeros(packed.mlp_save_bytes(M), dtype=torch.uint8, device=dev)
+    raw = packed.mlp_forward(pn, rays.to(dev), z.to(dev), save=save)
+    torch.cuda.synchronize()
+    raw = raw.cpu().reshape(-1, 4)
+    pts = (rays[:, None, 0:3] + rays[:, None, 3:6] * z[:, :, None]).reshape(-1, 3)
+    vd = rays[:, None, 8:11].expand(n_rays, S, 3).reshape(-1, 3)
+    with torch.no_grad():
+        hs, feat, hv, raw_ref = oracle_intermediates(p, "model", pts, vd)
+    buf = save.cpu().numpy()
+    groups = (M + 255) // 256
+    print(f"--- forward: points={M} groups={groups}")
+    for slot, (nm, ref) in enumerate(zip(["h1", "h2", "h3", "h4", "h5", "h6", "h7", "h8", "feat"], hs + [feat])):
+        got = np.concatenate([decode_image(buf, g, slot, 256) for g in range(groups)], 0)[:M]
+        err = np.abs(got - ref.numpy())
+        print(f"  {nm}: max|ref|={np.abs(ref.numpy()).max():.4f} maxerr={err.max():.5f} meanerr={err.mean():.6f}")
+    got = np.concatenate([decode_image(buf, g, 9, 128) for g in range(groups)], 0)[:M]
+    print(f"  hv: maxerr={np.abs(got - hv.numpy()).max():.5f}")
+    err = (raw - raw_ref).abs()
+    print(f"  raw: max|ref|={raw_ref.abs().max():.4f} maxerr={err.max():.5f} per-channel {err.max(0).values.tolist()}")
+    raw2 = packed.mlp_forward(pn, rays.to(dev), z.to(dev)).cpu().reshape(-1, 4)
+    print("  save vs nosave identical:", bool((raw2 == raw).all()), " finite:", bool(torch.isfinite(raw).all()))
     n_rays = 16384
     rays = synth_rays(n_rays, 12).to(dev)
     for S in (64, 192):
         z = torch.sort(2.0 + 4.0 * torch.rand(n_rays, S, device=dev), -1).values.contiguous()
-        for pingpong in (False, True):
+        save = torch.empty(packed.mlp_save_bytes(n_rays * S), dtype=torch.uint8, device=dev)
+        for name, kw in (("nosave", dict()), ("save", dict(save=save))):
             for _ in range(2):
-                packed.mlp_forward(pn, rays, z, pingpong=pingpong)
+                packed.mlp_forward(pn, rays, z, **kw)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(5):
-                packed.mlp_forward(pn, rays, z, pingpong=pingpong)
+                packed.mlp_forward(pn, rays, z, **kw)
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 5
             pts = n_rays * S
-            print(f"timing S={S} pingpong={pingpong}: {ms:.3f} ms  {pts / ms / 1e6:.3f} Gpts/s  {pts * 1.186816e6 / ms / 1e9:.1f} TFLOP/s")
+            print(f"timing S={S} {name}: {ms:.3f} ms  {pts / ms / 1e6:.3f} Gpts/s  {pts * 1.186816e6 / ms / 1e9:.1f} TFLOP/s")
+        del save
 
 
 if __name__ == "__main__":

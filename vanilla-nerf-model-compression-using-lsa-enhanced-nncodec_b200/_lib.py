@@ -14,10 +14,8 @@ _PROTOS = {
     "nerfq_num_channels": (c_int, []),
     "nerfq_pack_net": (c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_float), c_int, c_void_p]),
     "nerfq_set_scale_bias": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
-    "nerfq_mlp_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "nerfq_mlp_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "nerfq_mlp_save_bytes": (c_ull, [c_ll]),
-    "nerfq_mlp3_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p]),
-    "nerfq_mlp3_save_bytes": (c_ull, [c_ll]),
 }
 
 _lib = None

@@ -1,4 +1,4 @@
-// Fused NeRF MLP backward into the LSA scales on tcgen05 tensor cores (sm_100a), third generation.
+// Fused NeRF MLP backward into the LSA scales on tcgen05 tensor cores (sm_100a).
 //
 // Replaces torch autograd over NeRF.forward with ScaledLinear layers (utils.py:57-80, transforms.py:104-111) when
 // only `weight_scaling` requires grad (framework/pytorch_model/__init__.py:1129-1145, run_nerf.py:756).  For a layer
@@ -340,10 +340,10 @@ __global__ void mlp3_backward_finalize_kernel(uint8_t* packed, float* __restrict
 }  // namespace nerfq
 
 static unsigned long long* g_trace3b = nullptr;
-// Profiling aid (not part of include/nerfq.h): see nerfq_mlp3_set_trace.
-extern "C" void nerfq_mlp3_set_trace_bwd(unsigned long long* buf) { g_trace3b = buf; }
+// Profiling aid (not part of include/nerfq.h): see nerfq_mlp_set_trace.
+extern "C" void nerfq_mlp_set_trace_bwd(unsigned long long* buf) { g_trace3b = buf; }
 
-extern "C" int nerfq_mlp3_backward(const void* packed, const float* d_raw, const float* raw, const void* save, long long n_points,
+extern "C" int nerfq_mlp_backward(void* packed, const float* d_raw, const float* raw, const void* save, long long n_points,
                                    float* d_scale, int max_ctas, cudaStream_t stream) {
     using namespace nerfq;
     if (n_points == 0) return 0;
@@ -357,7 +357,7 @@ extern "C" int nerfq_mlp3_backward(const void* packed, const float* d_raw, const
     const int grid = n_groups < sms ? n_groups : sms;
     // the kernel accumulates s*ds into a scratch array of the packed buffer (zeroed by nerfq_pack_net and by every
     // finalize), the finalize kernel divides by the LSA scale and adds into d_scale
-    uint8_t* pk = (uint8_t*)const_cast<void*>(packed);
+    uint8_t* pk = (uint8_t*)packed;
     Bwd3Params prm{(const uint8_t*)packed, d_raw, raw, (const uint8_t*)save, reinterpret_cast<float*>(pk + kOffGradTmp3), n_points, n_groups,
                    g_trace3b, prog};
     if (g_trace3b) {

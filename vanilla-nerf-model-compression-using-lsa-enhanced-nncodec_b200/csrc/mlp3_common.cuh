@@ -1,4 +1,4 @@
-// Device-side pieces shared by the third-generation fused MLP kernels (mlp3_fwd.cu, mlp3_bwd.cu):
+// Device-side pieces shared by the fused MLP kernels (mlp3_fwd.cu, mlp3_bwd.cu):
 // CTA shape, shared-memory map, barrier indices, the weight loader and the MMA-issuing loop.
 #pragma once
 #include "mlp3_layout.h"

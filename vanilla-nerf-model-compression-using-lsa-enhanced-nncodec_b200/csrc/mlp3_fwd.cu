@@ -1,4 +1,4 @@
-// Fused positional-encoding + NeRF MLP forward on tcgen05 tensor cores (sm_100a), third generation.
+// Fused positional-encoding + NeRF MLP forward on tcgen05 tensor cores (sm_100a).
 //
 // Replaces, for one network and M = n_rays*S sample points:
 //   pts = o + d*z                                   run_nerf.py:408,430
@@ -261,9 +261,9 @@ static unsigned long long* g_trace3 = nullptr;
 static int g_trace3_flags = 0;
 // Profiling aid (not part of include/nerfq.h): when set, launches use the tracing instantiation of the kernels, which
 // writes 8 cycle counters per CTA into this device buffer (see profiles/trace_v3.py).
-extern "C" void nerfq_mlp3_set_trace(unsigned long long* buf, int flags) { g_trace3 = buf; g_trace3_flags = flags; }
+extern "C" void nerfq_mlp_set_trace(unsigned long long* buf, int flags) { g_trace3 = buf; g_trace3_flags = flags; }
 
-extern "C" int nerfq_mlp3_forward(const void* packed, const float* rays, const float* z, long long n_rays, int samples_per_ray,
+extern "C" int nerfq_mlp_forward(const void* packed, const float* rays, const float* z, long long n_rays, int samples_per_ray,
                                   float* raw, void* save, int max_ctas, cudaStream_t stream) {
     using namespace nerfq;
     if (n_rays == 0) return 0;
@@ -286,7 +286,7 @@ extern "C" int nerfq_mlp3_forward(const void* packed, const float* rays, const f
     return save ? launch(mlp3_forward_kernel<true, false>) : launch(mlp3_forward_kernel<false, false>);
 }
 
-extern "C" unsigned long long nerfq_mlp3_save_bytes(long long n_points) {
+extern "C" unsigned long long nerfq_mlp_save_bytes(long long n_points) {
     using namespace nerfq;
     const long long n_groups = (n_points + kGroupPts - 1) / kGroupPts;
     return (unsigned long long)n_groups * kSave3GroupBytes;

@@ -1,4 +1,4 @@
-// Fused NeRF MLP, third generation ("channels on TMEM lanes", table-driven control).
+// Fused NeRF MLP kernels: operand layouts and the per-group program ("channels on TMEM lanes", table-driven control).
 //
 //   D[o][n] = sum_k A[o][k] * B[n][k]
 //   A = weight chunk    [128 output channels x 64 k]  two K-major SWIZZLE_64B stages of 8 KB, streamed (16 KB)
@@ -227,7 +227,7 @@ inline Prog3Bwd make_prog3_bwd() {
     return p;
 }
 
-// ---- packed network buffer: v3 images appended after the first-generation fields -----------------
+// ---- packed network buffer: weight images after the small fields of net_layout.h -----------------
 constexpr size_t kOffFwd3Image = (kPackedBytes + 1023) / 1024 * 1024;
 constexpr size_t kOffBwd3Image = kOffFwd3Image + kFwd3ImageBytes;
 constexpr size_t kOffGradTmp3 = kOffBwd3Image + kBwd3ImageBytes;          // float[2440] backward scratch (kept zeroed)

@@ -1,5 +1,5 @@
-// Packing of one NeRF network into the format the fused MLP kernels stream (net_layout.h):
-// weight levels -> fp16 K-major SWIZZLE_64B stage images of W (forward) and W^T (backward),
+// Packing of one NeRF network into the format the fused MLP kernels stream (mlp3_layout.h):
+// weight levels -> fp16 K-major SWIZZLE_64B stage images of W (forward) and W^T (backward) in consumption order,
 // plus the per-channel epilogue constants {delta * lsa_scale, bias}.
 //
 // The reference keeps, per Linear layer, a float32 `weight` that holds dequantised values
@@ -23,8 +23,6 @@ struct PackParams {
     int src_is_int32;
 };
 
-__device__ __constant__ MmaStep kFwdTab[kFwdSteps] = NERFQ_FWD_STEP_TABLE;
-__device__ __constant__ MmaStep kBwdTab[kBwdSteps] = NERFQ_BWD_STEP_TABLE;
 __device__ __constant__ int kInDev[kNumLayers] = {63, 256, 256, 256, 256, 319, 256, 256, 256, 256, 283, 128};
 __device__ __constant__ int kOutDev[kNumLayers] = {256, 256, 256, 256, 256, 256, 256, 256, 1, 256, 128, 3};
 __device__ __constant__ int kChDev[kNumLayers] = {0, 256, 512, 768, 1024, 1280, 1536, 1792, kChAlpha, kChFeature, kChViews, kChRgb};
@@ -34,43 +32,7 @@ __device__ __forceinline__ float load_w(const PackParams& p, int layer, int idx)
                           : reinterpret_cast<const float*>(p.w[layer])[idx];
 }
 
-// grid = kFwdStages + kBwdStages blocks; block b packs one stage.
-__global__ void pack_images_kernel(const PackParams p) {
-    const bool bwd = blockIdx.x >= kFwdStages;
-    int sidx = bwd ? blockIdx.x - kFwdStages : blockIdx.x;
-    const MmaStep* tab = bwd ? kBwdTab : kFwdTab;
-    const int nsteps = bwd ? kBwdSteps : kFwdSteps;
-    uint32_t off = 0;
-    int s = 0;
-    for (; s < nsteps; ++s) {
-        if (sidx < tab[s].stages) break;
-        sidx -= tab[s].stages;
-        off += tab[s].stages * tab[s].n * kStageRowBytes;
-    }
-    const MmaStep st = tab[s];
-    off += sidx * st.n * kStageRowBytes;
-    uint8_t* dst = p.packed + (bwd ? kOffBwdImage : kOffFwdImage) + off;
-    const int in = kInDev[st.layer];
-    for (int item = threadIdx.x; item < st.n * 4; item += blockDim.x) {
-        const int n = item >> 2, chunk = item & 3;
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int kk = sidx * kStageK + chunk * 8 + e;     // position along K within the step
-            float x = 0.0f;
-            if (kk < st.ncols) {
-                // forward: B[n][kk] = W[n][col0 + kk];   backward: B[n][kk] = W[o = kk][col0 + n]
-                x = bwd ? load_w(p, st.layer, kk * in + st.col0 + n) : load_w(p, st.layer, n * in + st.col0 + kk);
-            }
-            v[e] = x;
-        }
-        uint4 q;
-        q.x = pack_half2(v[0], v[1]); q.y = pack_half2(v[2], v[3]); q.z = pack_half2(v[4], v[5]); q.w = pack_half2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(dst + sw64_offset(n, chunk)) = q;
-    }
-}
-
-// ---- v3 images ("channels on lanes", mlp3_layout.h): stages of [128 rows x 32 k] in consumption order
+// ---- weight images ("channels on lanes", mlp3_layout.h): stages of [128 rows x 32 k] in consumption order
 // (step, half, k stage); two consecutive stages form one 16 KB chunk ----
 struct Step3Tables {
     Step3 fwd[kFwd3Steps];
@@ -178,7 +140,6 @@ extern "C" int nerfq_pack_net(void* packed, const void* const* weights12, const 
     }
     p.packed = reinterpret_cast<uint8_t*>(packed);
     p.src_is_int32 = src_is_int32;
-    pack_images_kernel<<<kFwdStages + kBwdStages, 256, 0, stream>>>(p);
     Step3Tables tabs;
     for (int i = 0; i < kFwd3Steps; ++i) tabs.fwd[i] = kFwd3[i];
     for (int i = 0; i < kBwd3Steps; ++i) tabs.bwd[i] = kBwd3[i];

@@ -36,7 +36,6 @@ _PROTOS = {
                                    _c.c_float, _c.c_void_p, _c.c_void_p]),
     "nerfq_mse_grad": (_c.c_int, [_c.c_void_p] * 3 + [_c.c_longlong] + [_c.c_void_p] * 4),
     "nerfq_mlp_backward": (_c.c_int, [_c.c_void_p] * 4 + [_c.c_longlong, _c.c_void_p, _c.c_int, _c.c_void_p]),
-    "nerfq_mlp3_backward": (_c.c_int, [_c.c_void_p] * 4 + [_c.c_longlong, _c.c_void_p, _c.c_int, _c.c_void_p]),
 }
 _bound = False
 
@@ -184,15 +183,12 @@ def mse_grad(rgb: torch.Tensor, rgb0: Optional[torch.Tensor], target: torch.Tens
 
 
 def mlp_backward(net: PackedNet, d_raw: torch.Tensor, raw: torch.Tensor, save: torch.Tensor, d_scale: Optional[torch.Tensor] = None,
-                 max_ctas: int = 0, impl: Optional[int] = None) -> torch.Tensor:
+                 max_ctas: int = 0) -> torch.Tensor:
     """Accumulates d loss / d lsa_scale (flat [2436], kernel channel order) for one network."""
     n_points = raw.shape[0] * raw.shape[1]
     d_raw, raw = _f32(d_raw, *raw.shape), _f32(raw)
     if d_scale is None:
         d_scale = torch.zeros(2436, dtype=torch.float32, device=raw.device)
-    from .packed import IMPL
-    impl = IMPL["version"] if impl is None else impl
-    fn = L().nerfq_mlp3_backward if impl == 3 else L().nerfq_mlp_backward
-    _lib.check(fn(net.ptr, d_raw.data_ptr(), raw.data_ptr(), save.data_ptr(), n_points, d_scale.data_ptr(), max_ctas, _stream()),
-               "nerfq_mlp_backward")
+    _lib.check(L().nerfq_mlp_backward(net.ptr, d_raw.data_ptr(), raw.data_ptr(), save.data_ptr(), n_points, d_scale.data_ptr(), max_ctas,
+                                      _stream()), "nerfq_mlp_backward")
     return d_scale

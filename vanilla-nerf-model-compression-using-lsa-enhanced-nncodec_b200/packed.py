@@ -76,30 +76,18 @@ class PackedNet:
         return self.buf.data_ptr()
 
 
-IMPL = {"version": int(__import__("os").environ.get("NERFQ_MLP_IMPL", "1"))}      # 3: channels-on-lanes kernels (mlp3_*.cu); 1: first-generation kernels (mlp_*.cu)
-
-
-def mlp_save_bytes(n_points: int, impl: Optional[int] = None) -> int:
-    impl = IMPL["version"] if impl is None else impl
-    if impl == 3:
-        return int(_lib.lib().nerfq_mlp3_save_bytes(n_points))
+def mlp_save_bytes(n_points: int) -> int:
     return int(_lib.lib().nerfq_mlp_save_bytes(n_points))
 
 
 def mlp_forward(net: PackedNet, rays: torch.Tensor, z: torch.Tensor, save: Optional[torch.Tensor] = None,
-                pingpong: bool = False, max_ctas: int = 0, impl: Optional[int] = None) -> torch.Tensor:
+                max_ctas: int = 0) -> torch.Tensor:
     """raw[N,S,4] = MLP(gamma(o + d z), gamma(viewdir)) for rays [N,11] and depths z [N,S]."""
     assert rays.is_cuda and rays.dtype == torch.float32 and rays.shape[1] == 11 and rays.is_contiguous()
     assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous() and z.shape[0] == rays.shape[0]
     n, s = z.shape
     raw = torch.empty((n, s, 4), dtype=torch.float32, device=rays.device)
-    impl = IMPL["version"] if impl is None else impl
-    if impl == 3:
-        _lib.check(_lib.lib().nerfq_mlp3_forward(net.ptr, rays.data_ptr(), z.data_ptr(), n, s, raw.data_ptr(),
-                                                 save.data_ptr() if save is not None else None, max_ctas, _stream()),
-                   "nerfq_mlp3_forward")
-        return raw
     _lib.check(_lib.lib().nerfq_mlp_forward(net.ptr, rays.data_ptr(), z.data_ptr(), n, s, raw.data_ptr(),
-                                            save.data_ptr() if save is not None else None, int(pingpong), max_ctas,
-                                            _stream()), "nerfq_mlp_forward")
+                                            save.data_ptr() if save is not None else None, max_ctas, _stream()),
+               "nerfq_mlp_forward")
     return raw

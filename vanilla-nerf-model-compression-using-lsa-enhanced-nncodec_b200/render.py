@@ -28,7 +28,7 @@ img2mse = lambda x, y: torch.mean((x - y) ** 2)
 mse2psnr = lambda x: -10. * torch.log(x) / torch.log(torch.tensor([10.], device=x.device))
 to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)
 
-TUNING = {"pingpong": True, "max_ctas": 0}      # kernel scheduling knobs (bench/profiling)
+TUNING = {"max_ctas": 0}      # kernel scheduling knob (bench/profiling)
 DATA_PARALLEL = {"enabled": False}              # all-reduce (mean) the LSA-scale gradients over torch.distributed
 
 
@@ -62,7 +62,7 @@ def run_network(inputs, viewdirs, fn, embed_fn=None, embeddirs_fn=None, netchunk
     z = torch.zeros((n * s, 1), dtype=torch.float32, device=pts.device)
     with torch.no_grad():
         pn = _refresh(fn, _scale_flat(fn))
-        raw = packed.mlp_forward(pn, rays, z, pingpong=TUNING["pingpong"], max_ctas=TUNING["max_ctas"])
+        raw = packed.mlp_forward(pn, rays, z, max_ctas=TUNING["max_ctas"])
     return raw.reshape(n, s, 4)
 
 
@@ -117,14 +117,14 @@ class _Cfg:
 
 
 def _forward_pipeline(cfg: _Cfg, sc0, sc1, save: bool):
-    pp, mc = TUNING["pingpong"], TUNING["max_ctas"]
+    mc = TUNING["max_ctas"]
     rays = cfg.rays
     n = rays.shape[0]
     dev = rays.device
     pn0 = _refresh(cfg.net0, sc0)
     z0 = ops.coarse_depths(rays, cfg.S, cfg.lindisp, cfg.t_rand)
     save0 = torch.empty(packed.mlp_save_bytes(n * cfg.S), dtype=torch.uint8, device=dev) if save else None
-    raw0 = packed.mlp_forward(pn0, rays, z0, save=save0, pingpong=pp, max_ctas=mc)
+    raw0 = packed.mlp_forward(pn0, rays, z0, save=save0, max_ctas=mc)
     rgb0, disp0, acc0, w0, _ = ops.composite_fwd(raw0, z0, rays, cfg.white, cfg.noise0)
     st = dict(z0=z0, raw0=raw0, save0=save0, pn0=pn0)
     if cfg.Ni > 0:
@@ -132,7 +132,7 @@ def _forward_pipeline(cfg: _Cfg, sc0, sc1, save: bool):
         pn1 = _refresh(net1, sc1 if cfg.net1 is not None else sc0)
         z1, z_std, _ = ops.sample_fine(z0, w0, cfg.Ni, cfg.u)
         save1 = torch.empty(packed.mlp_save_bytes(n * (cfg.S + cfg.Ni)), dtype=torch.uint8, device=dev) if save else None
-        raw1 = packed.mlp_forward(pn1, rays, z1, save=save1, pingpong=pp, max_ctas=mc)
+        raw1 = packed.mlp_forward(pn1, rays, z1, save=save1, max_ctas=mc)
         rgb1, disp1, acc1, _, _ = ops.composite_fwd(raw1, z1, rays, cfg.white, cfg.noise1, want_weights=False)
         st.update(z1=z1, raw1=raw1, save1=save1, pn1=pn1)
         outs = (rgb1, disp1, acc1, rgb0, disp0, acc0, z_std, raw1)
