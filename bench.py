@@ -185,17 +185,15 @@ def run_cuda(args):
     t_h = t_h.pin_memory()
     rays_d = rays_h.to(dev)
     t_d = t_h.to(dev)
-    weight_keys = [k for k in master if k.endswith(".weight")]
+    sd0 = wrapper.state_dict()
+    restore_keys = [k for k in master if k.endswith(".weight") or k.endswith(".bias")]
+    restore_dst = [sd0[k] for k in restore_keys]
+    restore_src = [master[k] for k in restore_keys]
 
     def requantize():
         """BASELINE cfg2 'quantize' leg: float weights -> levels at qp (GPU kernel), repacked for the MLP."""
         with torch.no_grad():
-            sd = wrapper.state_dict()
-            for k in weight_keys:
-                sd[k].copy_(master[k])
-            for k in master:
-                if k.endswith(".bias"):
-                    sd[k].copy_(master[k])
+            torch._foreach_copy_(restore_dst, restore_src)          # the unquantised float weights and biases
         codec.quantize_model(wrapper, QP, QP_DENSITY, NONWEIGHT_QP)
 
     def lsa_step(rays, target, requant):
@@ -295,9 +293,9 @@ def run_cuda(args):
                         "h2d_bytes_per_step": int(rays_h.numel() * 4 + t_h.numel() * 4), "d2h_bytes_per_step": 4},
                 "clocks": clocks}
         # launches of OUR kernels per step: pack_rays 1, per network pass: set_scale_bias 1 + mlp_fwd 1 + composite_fwd 1,
-        # coarse_depths 1, sample_fine 1, bwd: 2 x (composite_bwd 1 + mlp_bwd 1); requantise: 24 tensors x 2 (w, b) x
-        # (absmax + quantize + dequantize) + 2 nets x 2 pack kernels
-        per_step = 1 + 2 * 3 + 1 + 1 + 2 * 2 + (24 * 2 * 3 + 4 if requant_each_step else 0)
+        # coarse_depths 1, sample_fine 1, mse_grad 0 (torch), bwd: 2 x (composite_bwd 1 + mlp_bwd 1 + finalize 1);
+        # requantise: absmax + quantize (batched over the 48 tensors) + 2 nets x 2 pack kernels
+        per_step = 1 + 2 * 3 + 1 + 1 + 2 * 3 + (2 + 4 if requant_each_step else 0)
         line["gpu_launches"] = per_step * args.steps
         if world == 1:
             rows = {k: {"ms": v[0], "tflops": v[1] / (v[0] * 1e-3) / 1e12} for k, v in kern.items()}

@@ -36,6 +36,13 @@ int nerfq_stepsize(int qp, int qp_density, float* out);
 int nerfq_quantize_urq(const float* w, int32_t* lvl, long long n, int qp, int qp_density, int* qp_used,
                        void* workspace4, nerfq_stream_t stream);
 
+/* The same for `count` (<= 64) tensors in one launch pair -- every tensor of a model, as run_ft_and_lsa quantises
+ * and reconstructs them before tuning (nnc_core/approximator/__init__.py:655-661).  w, lvl, rec, n, qp are HOST
+ * arrays of length count (device pointers / element counts / per-tensor qp); rec may be NULL, rec[t] may be NULL or
+ * alias w[t] (reconstruction level*delta in place).  workspace: 4*count bytes; qp_used: nullable device int[count]. */
+int nerfq_quantize_batch(const float* const* w, int32_t* const* lvl, float* const* rec, const long long* n, const int* qp,
+                         int count, int qp_density, int* qp_used, void* workspace, nerfq_stream_t stream);
+
 /* w = (float)level * delta(qp). */
 int nerfq_dequantize(const int32_t* lvl, float* w, long long n, int qp, int qp_density, nerfq_stream_t stream);
 

@@ -183,3 +183,24 @@ def test_quantizer_bit_exact(dev):
     e = torch.empty(0, dtype=torch.float32, device=dev)        # empty tensor
     lv, _ = ops.quantize_urq(e, -20, 2)
     assert lv.numel() == 0
+
+
+def test_quantizer_batch_bit_exact(dev):
+    """The batched launch (every tensor of a model at once, per-tensor qp, reconstruction in place) gives the same
+    levels, clipped qps and reconstructed values as the C oracle tensor by tensor."""
+    ops = _ops()
+    from oracle import quant_oracle as qo
+    rng = np.random.default_rng(7)
+    shapes = [(256, 63), (256,), (256, 256), (256,), (256, 319), (1, 256), (1,), (128, 283), (3, 128), (3,), (70001,)]
+    for qp in (-38, -20, -10):
+        ws = [(rng.standard_normal(s) * 0.2).astype(np.float32) for s in shapes] + [np.array([3e4, -1.0, 0.3], dtype=np.float32)]
+        qps = [qp if w.ndim == 2 else -75 for w in ws]
+        ts = [torch.from_numpy(w.copy()).to(dev) for w in ws]
+        lv, used = ops.quantize_batch(ts, qps, 2, reconstruct_in_place=True)
+        used = used.cpu().numpy()
+        for i, w in enumerate(ws):
+            lv_ref, used_ref = qo.quant_urq(w, qps[i], 2)
+            assert int(used[i]) == used_ref, (i, qp)
+            assert (lv[i].cpu().numpy() == lv_ref).all(), (i, qp)
+            assert (ts[i].cpu().numpy() == qo.dequant(lv_ref, used_ref, 2)).all(), (i, qp)
+    assert int(used[-1]) > -75                                  # the last tensor forces the qp clip

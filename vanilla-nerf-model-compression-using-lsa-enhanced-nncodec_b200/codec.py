@@ -17,26 +17,43 @@ from . import ops
 from .model import NeRF
 
 
+def _quantize_nets(nets, qp: int, qp_density: int, nonweight_qp: int):
+    """One launch pair for every weight and bias of `nets`: levels out, parameters overwritten with level*delta."""
+    tensors, qps = [], []
+    for net in nets:
+        for layer in net.layers():
+            tensors += [layer.weight.data, layer.bias.data]
+            qps += [qp, nonweight_qp]
+    for x in tensors:
+        assert x.dtype == torch.float32 and x.is_contiguous()
+    outs = []
+    for i in range(0, len(tensors), 64):
+        lv, _ = ops.quantize_batch(tensors[i:i + 64], qps[i:i + 64], qp_density, reconstruct_in_place=True)
+        outs += lv
+    step = ops.stepsize(qp, qp_density)
+    res, k = [], 0
+    for net in nets:
+        out, levels = {}, []
+        for i, layer in enumerate(net.layers()):
+            out[f"{i}.weight"], out[f"{i}.bias"] = outs[k], outs[k + 1]
+            levels.append(outs[k])
+            k += 2
+        net.quant_levels, net.quant_steps = levels, [step] * 12
+        net._packed = None         # (the kernel wrote through raw pointers: torch version counters did not move)
+        res.append(out)
+    return res
+
+
 @torch.no_grad()
 def quantize_net(net: NeRF, qp: int, qp_density: int = 2, nonweight_qp: int = -75) -> Dict[str, torch.Tensor]:
-    levels, steps, out = [], [], {}
-    for i, layer in enumerate(net.layers()):
-        lv, used = ops.quantize_urq(layer.weight.detach().float(), qp, qp_density)
-        levels.append(lv)
-        steps.append(ops.stepsize(qp, qp_density))
-        layer.weight.copy_(ops.dequantize(lv, qp, qp_density))
-        lb, _ = ops.quantize_urq(layer.bias.detach().float(), nonweight_qp, qp_density)
-        layer.bias.copy_(ops.dequantize(lb, nonweight_qp, qp_density))
-        out[f"{i}.weight"], out[f"{i}.bias"] = lv, lb
-    net.quant_levels, net.quant_steps = levels, steps
-    return out
+    return _quantize_nets([net], qp, qp_density, nonweight_qp)[0]
 
 
 @torch.no_grad()
 def quantize_model(wrapper, qp: int, qp_density: int = 2, nonweight_qp: int = -75):
     """Quantise + reconstruct both networks of a NeRFWrapper in place; returns {net: {tensor: int32 levels}}."""
-    return {"model": quantize_net(wrapper.model, qp, qp_density, nonweight_qp),
-            "model_fine": quantize_net(wrapper.model_fine, qp, qp_density, nonweight_qp)}
+    a, b = _quantize_nets([wrapper.model, wrapper.model_fine], qp, qp_density, nonweight_qp)
+    return {"model": a, "model_fine": b}
 
 
 @torch.no_grad()

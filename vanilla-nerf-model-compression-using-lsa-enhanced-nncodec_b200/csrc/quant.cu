@@ -86,9 +86,78 @@ __global__ void dequantize_kernel(const int32_t* __restrict__ lvl, float* __rest
     }
 }
 
+// ---- batched form: every tensor of a model in one launch pair ------------------------------------------
+constexpr int kMaxBatch = 64;
+struct BatchDesc {
+    const float* w[kMaxBatch];
+    int32_t* lvl[kMaxBatch];
+    float* rec[kMaxBatch];          // nullable per tensor; may alias w
+    long long n[kMaxBatch];
+    int qp[kMaxBatch];
+    int count;
+    int qp_density;
+};
+
+__global__ void absmax_batch_kernel(const __grid_constant__ BatchDesc b, unsigned int* __restrict__ out) {
+    const int t = blockIdx.y;
+    const float* __restrict__ w = b.w[t];
+    const long long n = b.n[t];
+    unsigned int m = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = max(m, __float_as_uint(fabsf(w[i])));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out + t, m);
+}
+
+__global__ void quantize_batch_kernel(const __grid_constant__ BatchDesc b, const unsigned int* __restrict__ absmax_bits,
+                                      int* __restrict__ qp_used) {
+    const int t = blockIdx.y;
+    const float* w = b.w[t];
+    int32_t* __restrict__ lvl = b.lvl[t];
+    float* rec = b.rec[t];
+    const long long n = b.n[t];
+    const int q = clip_qp(__uint_as_float(absmax_bits[t]), b.qp[t], b.qp_density);
+    const float d = stepsize(q, b.qp_density);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && qp_used) qp_used[t] = q;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float x = w[i];
+        const int m = (int)__fadd_rn(__fdiv_rn(fabsf(x), d), 0.5f);
+        const int l = x < 0.0f ? -m : m;
+        lvl[i] = l;
+        if (rec) rec[i] = __fmul_rn((float)l, d);
+    }
+}
+
 }  // namespace nerfq
 
 using namespace nerfq;
+
+// Quantise (and optionally reconstruct, rec[t] != NULL, in place allowed) `count` tensors with one launch pair.
+// All arrays are HOST arrays of length count holding device pointers / sizes / qps; workspace: 4*count bytes of
+// device memory; qp_used: nullable device int[count].
+extern "C" int nerfq_quantize_batch(const float* const* w, int32_t* const* lvl, float* const* rec, const long long* n, const int* qp,
+                                    int count, int qp_density, int* qp_used, void* workspace, cudaStream_t stream) {
+    if (count == 0) return 0;
+    if (!w || !lvl || !n || !qp || !workspace || count < 0 || count > kMaxBatch || qp_density < 0 || qp_density > 8) return -1;
+    BatchDesc b{};
+    long long n_max = 0;
+    for (int t = 0; t < count; ++t) {
+        if (!w[t] || !lvl[t] || n[t] < 0) return -1;
+        b.w[t] = w[t]; b.lvl[t] = lvl[t]; b.rec[t] = rec ? rec[t] : nullptr; b.n[t] = n[t]; b.qp[t] = qp[t];
+        if (n[t] > n_max) n_max = n[t];
+    }
+    b.count = count;
+    b.qp_density = qp_density;
+    long long bx = (n_max + 1023) / 1024;
+    if (bx < 1) bx = 1;
+    if (bx > 37) bx = 37;            // 37 x 4 = 148: with the per-tensor grid dimension the launch covers every SM
+    cudaMemsetAsync(workspace, 0, 4 * (size_t)count, stream);
+    const dim3 grid((unsigned)bx, (unsigned)count);
+    absmax_batch_kernel<<<grid, 256, 0, stream>>>(b, reinterpret_cast<unsigned int*>(workspace));
+    quantize_batch_kernel<<<grid, 256, 0, stream>>>(b, reinterpret_cast<const unsigned int*>(workspace), qp_used);
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
 
 extern "C" int nerfq_stepsize(int qp, int qp_density, float* out) {
     if (!out || qp_density < 0 || qp_density > 8) return -1;

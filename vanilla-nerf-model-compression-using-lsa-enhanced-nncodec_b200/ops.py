@@ -25,6 +25,8 @@ def _f32(t: torch.Tensor, *shape) -> torch.Tensor:
 _PROTOS = {
     "nerfq_stepsize": (_c.c_int, [_c.c_int, _c.c_int, _c.POINTER(_c.c_float)]),
     "nerfq_quantize_urq": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    "nerfq_quantize_batch": (_c.c_int, [_c.POINTER(_c.c_void_p), _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_longlong),
+                                        _c.POINTER(_c.c_int), _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "nerfq_dequantize": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_void_p]),
     "nerfq_coarse_depths": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "nerfq_composite_fwd": (_c.c_int, [_c.c_void_p] * 4 + [_c.c_int, _c.c_longlong, _c.c_int] + [_c.c_void_p] * 6),
@@ -66,6 +68,28 @@ def quantize_urq(w: torch.Tensor, qp: int, qp_density: int):
     _lib.check(L().nerfq_quantize_urq(w.data_ptr(), lvl.data_ptr(), w.numel(), int(qp), int(qp_density), ws[1:].data_ptr(),
                                       ws.data_ptr(), _stream()), "nerfq_quantize_urq")
     return lvl, ws[1:]
+
+
+def quantize_batch(tensors: Sequence[torch.Tensor], qps: Sequence[int], qp_density: int, reconstruct_in_place: bool = False,
+                   levels_out: Optional[Sequence[torch.Tensor]] = None):
+    """Quantise many float32 tensors with one launch pair: returns (list of int32 level tensors, qp_used int32[T]).
+    reconstruct_in_place overwrites each input with level*delta (what `rec(approx(x))` yields in the reference)."""
+    t = len(tensors)
+    assert t == len(qps) and 0 < t <= 64
+    dev = tensors[0].device
+    for x in tensors:
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    lv = list(levels_out) if levels_out is not None else [torch.empty(x.shape, dtype=torch.int32, device=dev) for x in tensors]
+    ws = torch.empty(2 * t, dtype=torch.int32, device=dev)
+    vp = _c.c_void_p * t
+    w_arr = vp(*[x.data_ptr() for x in tensors])
+    l_arr = vp(*[x.data_ptr() for x in lv])
+    r_arr = vp(*[x.data_ptr() for x in tensors]) if reconstruct_in_place else None
+    n_arr = (_c.c_longlong * t)(*[x.numel() for x in tensors])
+    q_arr = (_c.c_int * t)(*[int(q) for q in qps])
+    _lib.check(L().nerfq_quantize_batch(w_arr, l_arr, r_arr, n_arr, q_arr, t, int(qp_density), ws[t:].data_ptr(), ws.data_ptr(), _stream()),
+               "nerfq_quantize_batch")
+    return lv, ws[t:]
 
 
 def dequantize(lvl: torch.Tensor, qp: int, qp_density: int) -> torch.Tensor:
