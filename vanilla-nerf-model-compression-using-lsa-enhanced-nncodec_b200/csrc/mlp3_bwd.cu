@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
 
     if (warp < kCtrlWarps3) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 " NERFQ_REGS_CTRL3 ";");
-        if (warp == 0) {
-            loader3(sbase, prm.packed + kOffBwd3Image, kBwd3Chunks, n_iters);
+        if (warp == 0 || warp == 2) {
+            loader3(sbase, prm.packed + kOffBwd3Image, kBwd3Chunks, n_iters, warp >> 1);
         } else if (warp == 1) {
             if (n_iters > 0) issuer3<kBwd3Jobs, kTrace>(sbase, tmem_base, prm.prog.half, n_iters, false, prm.dbg);
         }

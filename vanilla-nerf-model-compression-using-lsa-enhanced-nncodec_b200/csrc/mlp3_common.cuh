@@ -6,7 +6,7 @@
 
 namespace nerfq {
 
-// warp 0: weight loader (and TMEM owner)   warp 1: MMA issuer   warps 2, 3: idle (they complete the control warp group)
+// warps 0, 2: weight loaders (warp 0 owns TMEM)   warp 1: MMA issuer   warp 3: idle
 // warps 4..19: epilogue; a warp may only touch TMEM lanes 32*(warp % 4).., so warp w owns lane quarter q = w & 3 and
 // point quarter pq = (w - 4) >> 2.
 // Registers: 20 warps are launched with 96 registers each; the control warp group then releases registers
@@ -75,12 +75,17 @@ __device__ __forceinline__ uint32_t setup3(uint8_t* smem, uint32_t sbase, int wa
 
 // ---- weight loader: the image is a stream of equal chunks in consumption order, repeated per group ----
 // Called by a whole converged warp (so that addresses stay in uniform registers); one elected lane issues.
-__device__ __forceinline__ void loader3(uint32_t sbase, const uint8_t* img, int n_chunks, int n_iters) {
+// One issuing thread sustains only ~30-37 B/clk of bulk copies (profiles/r01_umma_rate2_bulk_issue_parallelism.log)
+// against the 32 B/clk the MMAs consume, so kLoaders3 warps share the stream: warp `which` copies the chunks with
+// sequence number = which (mod kLoaders3).
+constexpr int kLoaders3 = 2;
+__device__ __forceinline__ void loader3(uint32_t sbase, const uint8_t* img, int n_chunks, int n_iters, int which) {
     auto bar = [&](int i) { return sbase + kS3Bars + 8u * i; };
     uint32_t seq = 0;
     for (int it = 0; it < n_iters; ++it) {
         const uint8_t* src = img;
         for (int c = 0; c < n_chunks; ++c, ++seq, src += kChunk3Bytes) {
+            if ((int)(seq % kLoaders3) != which) continue;
             const uint32_t slot = seq & (kSlots3 - 1), par = (seq >> 2) & 1;
             mbar_wait(bar(kB3WEmpty) + 8 * slot, par ^ 1);
             if (elect_one()) {

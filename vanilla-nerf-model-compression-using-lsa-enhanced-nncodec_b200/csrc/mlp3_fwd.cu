@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
     const int first = blockIdx.x, stride = gridDim.x;
     const int n_iters = first < prm.n_groups ? (prm.n_groups - first + stride - 1) / stride : 0;
 
-    if (warp == 0) {
-        loader3(sbase, prm.packed + kOffFwd3Image, kFwd3Chunks, n_iters);
+    if (warp == 0 || warp == 2) {
+        loader3(sbase, prm.packed + kOffFwd3Image, kFwd3Chunks, n_iters, warp >> 1);
     } else if (warp == 1) {
         if (n_iters > 0) issuer3<kFwd3Jobs, kTrace>(sbase, tmem_base, prm.prog.half, n_iters, true, prm.dbg);
     } else if (warp >= kCtrlWarps3) {
