@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                             if (gi < prm.n_points) prm.raw[4 * gi + 3] = sg;
                         }
                     }
+                    if (kSave && lane == 0) bulk_commit();      // empty group: keeps "two jobs ago" == "all but the newest group"
                     publish(kB3ActHi);
                     if (tracing) { const unsigned long long dt = clock64() - t0; t_job += dt; if (j == j_sel) t_sel += dt; }
                     continue;
@@ -191,7 +192,9 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                             if (tracing) t_sf += clock64() - t1;
                         }
                         if (kSave) {
-                            if (lane == 0) bulk_wait_read_all();
+                            // the rows about to be overwritten were handed to the bulk-store engine two jobs ago (the job
+                            // in between wrote the other 128 channels): all but the newest store group must have been read
+                            if (lane == 0) bulk_wait_read_but1();
                             __syncwarp();
                         }
                     }
