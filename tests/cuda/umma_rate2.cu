@@ -32,6 +32,7 @@ struct Args {
     int slots;       // slots per issuer
     int chunk;       // bulk copy bytes; bulk * lanes * slots * chunk <= 96 KB
     const uint8_t* src;          // >= 2 MB, L2 resident
+    uint8_t* dst;                // bulk-store target: 3 MB per CTA
     unsigned long long* out;     // per CTA: cycles, sts count, bulk count
 };
 
@@ -155,6 +156,22 @@ __global__ void __launch_bounds__(384, 1) rate2_kernel(const Args a) {
                 asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(raddr), "r"(1u) : "memory");
             }
         }
+    } else if (warp >= 1 && warp <= 3 && a.bulk < 0) {
+        // smem -> global bulk stores (what the forward kernel's activation saving does): keep `slots` groups in flight
+        if (warp - 1 < -a.bulk && lane == 0) {
+            uint8_t* dst = a.dst + ((size_t)blockIdx.x * 3 + (warp - 1)) * (1u << 20);
+            uint32_t issued = 0;
+            while (!*flag) {
+                bulk_s2g(dst + (issued & 63) * 16384, sbase + kRing + (warp - 1) * 16384, a.chunk);
+                bulk_commit();
+                ++issued;
+                if (a.slots == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                else if (a.slots == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+            }
+            bulk_wait_all();
+            n_bulk = issued;
+        }
     } else if (warp >= 1 && warp <= 3) {
         if (warp - 1 < a.bulk && lane < a.lanes) {
             const int issuer = (warp - 1) * a.lanes + lane;
@@ -204,33 +221,24 @@ int main() {
     uint8_t* d_src;
     cudaMalloc(&d_src, 4 << 20);
     cudaMemset(d_src, 0, 4 << 20);
+    uint8_t* d_dst;
+    cudaMalloc(&d_dst, (size_t)sms * 3 << 20);
     cudaFuncSetAttribute(rate2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     cudaFuncSetAttribute(rate2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     const char* names[] = {"none (spin)", "SS A K / B K   ", "SS A K / B MN  ", "TS A tmem / B K", "2CTA SS M=256  "};
     struct Exp { int mode, n, sts, bulk, lanes, slots, chunk; };
     std::vector<Exp> exps;
-    for (int mode : {0, 3}) exps.push_back({mode, 256, 0, 0, 1, 1, 16384});
-    exps.push_back({-1, 256, 8, 0, 1, 1, 16384});
-    exps.push_back({-1, 256, 0, 1, 1, 4, 16384});
-    exps.push_back({-1, 256, 0, 1, 1, 2, 32768});
-    exps.push_back({-1, 256, 0, 1, 1, 1, 65536});
-    exps.push_back({-1, 256, 0, 2, 1, 2, 16384});
-    exps.push_back({-1, 256, 0, 3, 1, 2, 16384});
-    exps.push_back({-1, 256, 0, 3, 1, 1, 32768});
-    exps.push_back({-1, 256, 0, 3, 1, 4, 8192});
-    exps.push_back({-1, 256, 0, 3, 1, 4, 4096});
-    exps.push_back({-1, 256, 0, 1, 4, 1, 16384});
-    exps.push_back({-1, 256, 0, 1, 6, 1, 16384});
-    exps.push_back({-1, 256, 0, 3, 2, 1, 16384});
-    exps.push_back({-1, 256, 0, 3, 4, 1, 8192});
-    for (int mode : {0, 3}) {
-        exps.push_back({mode, 256, 0, 3, 1, 2, 16384});
-        exps.push_back({mode, 256, 8, 3, 1, 2, 16384});
-        exps.push_back({mode, 256, 8, 1, 4, 1, 16384});
+    exps.push_back({0, 256, 0, 0, 1, 1, 16384});
+    for (int mode : {-1, 0, 1}) {
+        exps.push_back({mode, 256, 0, -1, 1, 4, 16384});
+        exps.push_back({mode, 256, 0, -3, 1, 4, 16384});
+        exps.push_back({mode, 256, 0, -3, 1, 4, 1024});
+        exps.push_back({mode, 256, 0, -3, 1, 4, 4096});
+        exps.push_back({mode, 256, 8, -3, 1, 4, 4096});
     }
     for (int grid : {sms}) {
         for (const Exp& e : exps) {
-            Args a{e.mode, e.n, 512, e.sts, e.bulk, e.lanes, e.slots, e.chunk, d_src, d_out};
+            Args a{e.mode, e.n, 512, e.sts, e.bulk, e.lanes, e.slots, e.chunk, d_src, d_dst, d_out};
             cudaMemset(d_out, 0, sms * 24);
             if (e.mode == 3) {
                 cudaLaunchConfig_t cfg{};

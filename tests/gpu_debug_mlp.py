@@ -40,14 +40,14 @@ def build_net(net, dev):
     return packed.PackedNet(ws, [delta] * 12, bs, ss), p
 
 ACT = 131072
-GROUP_BYTES = 9 * ACT + ACT // 2
+GROUP_BYTES = 10 * ACT
 
 
 def decode_image(buf_u8, group, slot, width):
-    """MN-major activation image -> [256 points, width channels] float32."""
+    """saved-activation slot ([16 point chunks][256 channels][16 points] fp16) -> [256 points, width channels] float32."""
     k = np.arange(width)[None, :]
     n = np.arange(256)[:, None]
-    off = (k >> 3) * 4096 + (n >> 6) * 1024 + (k & 7) * 128 + ((((n & 63) >> 3) ^ (k & 7)) << 4) + (n & 7) * 2
+    off = ((n >> 4) * 256 + k) * 32 + (n & 15) * 2
     base = group * GROUP_BYTES + slot * ACT
     u16 = buf_u8[base: base + ACT].view(np.uint16)
     return u16[off // 2].view(np.float16).astype(np.float32)

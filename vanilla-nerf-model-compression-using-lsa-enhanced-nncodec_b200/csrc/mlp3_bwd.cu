@@ -11,7 +11,8 @@
 // runs with input channels k on the TMEM lanes, so an epilogue thread owns ONE channel of the layer whose output the
 // accumulator is the gradient of: it masks with the saved forward activation (ReLU), accumulates its channel's
 // scale-gradient sums in registers (no cross-lane reduction), and writes the next GEMM's operand row.  Saved
-// activations are read straight from the forward kernel's HBM images (L2-prefetched one job ahead).
+// activations are read straight from the forward kernel's chunk-major HBM slots (coalesced 32-byte requests,
+// L2-prefetched two jobs ahead).
 // Gradients are tiny (1e-7..1e-3): each group is multiplied by a power of two that brings max|d_raw| into [8,16)
 // -- backpropagation is linear, the factor is exact and is divided out where the scale-gradient sums are flushed --
 // which keeps fp16's 11-bit significand for the operands without its range problem.
@@ -104,10 +105,9 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(which));
         };
-        // saved rows of this thread: 64 points of channel (chh) in image `slot` -> 8 x 16-byte pieces
+        // saved activations of this thread: channel chh of slot `slot`, its 8 chunks of 16 points start at point chunk 8*ph
         auto saved_row = [&](int g, int slot, uint32_t chh) {
-            return prm.save + (size_t)g * kSave3GroupBytes + (size_t)slot * kAct3Bytes + (chh >> 3) * kKGroup3 + (2 * ph) * kNGroup3 +
-                   (chh & 7u) * 128u;
+            return prm.save + (size_t)g * kSave3GroupBytes + (size_t)slot * kSave3SlotBytes + save3_offset(8 * ph, chh);
         };
         // one chunk of 16 points of this thread's channel.  d = gradient w.r.t. the layer output (fp32, from TMEM),
         // h = saved activations (8 x half2).  The elementwise work runs on packed halves:
@@ -141,9 +141,8 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                                  pk[4 * k + 2], pk[4 * k + 3]);
             }
         };
-        // The 16 points of chunk cc (0..7) of this thread's row are two 16-byte pieces at swizzled positions 2c^x and
-        // (2c+1)^x (x = channel & 7): one aligned 32-byte pair, in swapped order when x is odd.
-        auto pair_off = [&](int cc, uint32_t swz) { return (uint32_t)((cc >> 2) * kNGroup3) + (((uint32_t)((cc & 3) << 5)) ^ (swz & 0x60u)); };
+        // chunk cc (0..7) of this thread's 128 points: 32 bytes, 8 KB apart (mlp3_layout.h, save3_offset)
+        auto pair_off = [&](int cc, uint32_t) { return save3_offset(cc, 0); };
         // 64 KB slice of saved activations read by this team's i-th job of group g.  Team 0: views job (i = 0), then
         // jobs 0, 2, .., 16; team 1: jobs 1, 3, .., 17.  i past the end continues in the CTA's next group.
         const int team_jobs = team == 0 ? kBwd3Jobs / 2 + 1 : kBwd3Jobs / 2;
@@ -151,14 +150,15 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
             if (i >= team_jobs) { i -= team_jobs; g += stride; }
             if (g >= prm.n_groups) g = prm.n_groups - 1;
             const uint8_t* base = prm.save + (size_t)g * kSave3GroupBytes;
-            if (team == 0 && i == 0) return base + (size_t)9 * kAct3Bytes;
+            if (team == 0 && i == 0) return base + (size_t)9 * kSave3SlotBytes;
             const Job3 jn = prm.prog.job[team == 0 ? 2 * (i - 1) : 2 * i + 1];
-            return base + (size_t)jn.slot * kAct3Bytes + ((jn.flags & JB_HI_HALF) ? kAct3Bytes / 2 : 0);
+            return base + (size_t)jn.slot * kSave3SlotBytes + ((jn.flags & JB_HI_HALF) ? save3_offset(0, 128) : 0);
         };
         const int tl = (e & 7) * 32 + lane;        // thread index within the team: prefetches lines tl and tl + 256
+        // a job's 64 KB are 16 pieces of 4 KB (128 channels x 32 B), one per point chunk, 8 KB apart: 32 lines each
         auto prefetch_slice = [&](const uint8_t* sl) {
-            prefetch_l2_line(sl + 128 * tl);
-            prefetch_l2_line(sl + 128 * (tl + 256));
+            prefetch_l2_line(sl + (tl >> 5) * 8192 + (tl & 31) * 128);
+            prefetch_l2_line(sl + ((tl + 256) >> 5) * 8192 + (tl & 31) * 128);
         };
         float2 c_next = make_float2(1.f, 0.f);
         if (n_iters > 0) {
@@ -237,7 +237,6 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 const uint32_t row_addr = act + (chh >> 3) * kKGroup3 + (2 * ph) * kNGroup3 + (chh & 7u) * 128u;
                 const uint32_t swz = (chh & 7u) << 4;
                 prefetch_slice(slice_ptr(g, 2));
-                const bool odd = chh & 1u;
                 float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll 1
                 for (int cc = 0; cc < 8; ++cc) {
@@ -248,7 +247,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                         const float4 gq = ld_shared_v4f(pg_a + 16 * (ph * 128 + cc * 16 + i));
                         d[i] = fmaf(gq.x, w0, fmaf(gq.y, w1, gq.z * w2));
                     }
-                    chunk16(d, odd ? hp.b : hp.a, odd ? hp.a : hp.b, __float2half2_rn(c.x), true, true, row_addr, swz, cc, s1, s2);
+                    chunk16(d, hp.a, hp.b, __float2half2_rn(c.x), true, true, row_addr, swz, cc, s1, s2);
                 }
                 // ds * s = sum dY (y - b) = s1 - b * (sum dY);  s2 accumulated dY*es
                 publish(kB3ActLo);
@@ -269,7 +268,6 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 const uint32_t swz = (chh & 7u) << 4;
                 // saved activations: two chunks are requested before the accumulator is waited for, then each consumed
                 // slot is refilled with the chunk two ahead
-                const bool odd = chh & 1u;
                 H32 hh[2];
                 hh[0] = ldg_nc_32B(hrow + pair_off(0, swz));
                 hh[1] = ldg_nc_32B(hrow + pair_off(1, swz));
@@ -306,7 +304,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                     if (cc == 0 && (f & JB_WAIT_SF)) { mbar_wait(bar(kB3StageFree + (q >> 1)), ph_sf); ph_sf ^= 1; }
                     const H32 hp = hh[cc & 1];
                     if (cc < 6) hh[cc & 1] = ldg_nc_32B(hrow + pair_off(cc + 2, swz));       // refill with chunk cc + 2
-                    chunk16(d, odd ? hp.b : hp.a, odd ? hp.a : hp.b, es2, relu, write, row_addr, swz, cc, s1, s2);
+                    chunk16(d, hp.a, hp.b, es2, relu, write, row_addr, swz, cc, s1, s2);
                 }
                 if (write || team) publish(team ? kB3ActHi : kB3ActLo);
                 red_global_add_f32(prm.grad_tmp + jb.ch + cl, (s1 - c.y * (s2 / c.x)) * rinv);     // after the hand-over

@@ -14,8 +14,10 @@
 // dequantisation constants of ITS channel in registers and applies  y = acc * (delta * s[o]) + b[o], ReLU, fp16
 // conversion, storing 8 points per 16-byte shared-memory store into the next layer's operand tile.  The epilogue of
 // channels 0..127 overlaps the MMAs of channels 128..255 and vice versa.  The alpha head is reduced on CUDA cores
-// in the L7 epilogue; the rgb head is one more (3-of-128-row) MMA.  With `save` set every operand tile is also
-// streamed to HBM (bulk stores, one per 1 KB piece a warp owns) for the backward pass.
+// in the L7 epilogue; the rgb head is one more (3-of-128-row) MMA.  With `save` set the fp16 activations are also
+// written to HBM for the backward pass, straight from the registers that feed the shared-memory store, in a
+// chunk-major layout that makes every warp store 1 KB contiguous (mlp3_layout.h).  (Letting the bulk-copy engine read
+// the tile back out of shared memory competes with the MMA operand reads: 11 B/clk/SM, profiles/r01_umma_rate2_bulk_store_vs_mma.log.)
 #include <cuda_runtime.h>
 
 #include "mlp3_common.cuh"
@@ -155,7 +157,6 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                             if (gi < prm.n_points) prm.raw[4 * gi + 3] = sg;
                         }
                     }
-                    if (kSave && lane == 0) bulk_commit();      // empty group: keeps "two jobs ago" == "all but the newest group"
                     publish(kB3ActHi);
                     if (tracing) { const unsigned long long dt = clock64() - t0; t_job += dt; if (j == j_sel) t_sel += dt; }
                     continue;
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                 const bool relu = f & JB_RELU;
                 const uint32_t row_addr = act + (ch >> 3) * kKGroup3 + pq * kNGroup3 + (ch & 7u) * 128u;
                 const uint32_t swz = (ch & 7u) << 4;
+                uint8_t* save_ch = kSave ? save_g + (size_t)jb.slot * kSave3SlotBytes + save3_offset(0, ch) : nullptr;
                 uint32_t va[16], vb[16];
                 auto process = [&](const uint32_t (&v)[16], int cc) {
                     float y[16];
@@ -191,16 +193,12 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                             ph_sf ^= 1;
                             if (tracing) t_sf += clock64() - t1;
                         }
-                        if (kSave) {
-                            // the rows about to be overwritten were handed to the bulk-store engine two jobs ago (the job
-                            // in between wrote the other 128 channels): all but the newest store group must have been read
-                            if (lane == 0) bulk_wait_read_but1();
-                            __syncwarp();
-                        }
                     }
 #pragma unroll
                     for (int k = 0; k < 2; ++k)
                         st_shared_v4(row_addr + ((uint32_t)((cc * 2 + k) << 4) ^ swz), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+                    // the same 16 values go to the saved-activation slot: the warp's 32 channels are adjacent, 1 KB per store
+                    if (kSave) st_global_v8(save_ch + save3_offset(pq * 4 + cc, 0), pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
                     if (f & JB_ALPHA) {        // L7 is a ReLU layer: the head sees max(y, 0)
 #pragma unroll
                         for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.0f) * wa;
@@ -223,19 +221,6 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                     process(vb, 3);
                 }
                 if (tracing) { const unsigned long long dt = clock64() - t0; t_math += dt; if (j == j_sel) t_sel_math += dt; }
-                if (kSave) {
-                    // this warp's 4 pieces of 1 KB (8 channels x 64 points each) -> HBM image of slot jb.slot
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        const uint32_t piece = ((128u * hi + 32u * q) >> 3) * kKGroup3 + pq * kNGroup3;
-                        uint8_t* dst = save_g + (size_t)jb.slot * kAct3Bytes + piece;
-#pragma unroll
-                        for (int gk = 0; gk < 4; ++gk)
-                            bulk_s2g(dst + gk * kKGroup3, sbase + kS3Act + piece + gk * kKGroup3, kNGroup3);
-                        bulk_commit();
-                    }
-                }
                 if (f & JB_PE_AFTER) {          // the direction stage of this group has been accumulated
                     if (g + stride < prm.n_groups) {
                         write_pe_half(enc, pt, role, p);
@@ -250,7 +235,6 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
         if (tracing && prm.dbg) {
             if (e == 5) { prm.dbg[8 * blockIdx.x + 4] = t_acc; prm.dbg[8 * blockIdx.x + 5] = t_sf; prm.dbg[8 * blockIdx.x + 6] = t_job; prm.dbg[8 * blockIdx.x + 7] = t_math; prm.dbg[8 * 148 + 32 * blockIdx.x] = t_sel; prm.dbg[8 * 148 + 32 * blockIdx.x + 1] = t_sel_math; }
         }
-        if (kSave && lane == 0) bulk_wait_all();
     }
 
     tc_fence_before_sync();

@@ -233,7 +233,15 @@ constexpr size_t kOffBwd3Image = kOffFwd3Image + kFwd3ImageBytes;
 constexpr size_t kOffGradTmp3 = kOffBwd3Image + kBwd3ImageBytes;          // float[2440] backward scratch (kept zeroed)
 constexpr size_t kPacked3Bytes = kOffGradTmp3 + 4 * 2440;
 
-// ---- saved activations: per group 9 MN-major images of 128 KB (h1..h8, feature) + 64 KB (views hidden) ----
-constexpr size_t kSave3GroupBytes = 9 * (size_t)kAct3Bytes + kAct3Bytes / 2;
+// ---- saved activations (forward with `save`, read by the backward) ------------------------------------------
+// Per group of 256 points ten slots (h1..h8, feature, views hidden) of 128 KB, each laid out
+//   [16 point chunks of 16 points][256 channels][16 points] fp16      (the views slot uses channels 0..127 only)
+// so that the 32 lanes of an epilogue warp (32 consecutive channels, one 16-point chunk) write / read 1 KB of
+// contiguous memory per instruction -- full 128-byte lines both ways.
+constexpr int kSave3Slots = 10;
+constexpr size_t kSave3SlotBytes = 16 * 256 * 32;
+constexpr size_t kSave3GroupBytes = kSave3Slots * kSave3SlotBytes;
+// byte offset of (point chunk pc = point / 16, channel) inside a slot
+__host__ __device__ constexpr uint32_t save3_offset(uint32_t pc, uint32_t channel) { return (pc * 256u + channel) * 32u; }
 
 }  // namespace nerfq

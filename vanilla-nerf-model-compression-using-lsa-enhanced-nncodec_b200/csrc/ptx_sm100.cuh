@@ -214,6 +214,12 @@ __device__ __forceinline__ float4 ld_shared_v4f(uint32_t addr) {
 __device__ __forceinline__ void red_shared_add_f32(uint32_t addr, float v) {
     asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+// 32-byte global store (one full sector; a warp of consecutive addresses writes eight full lines)
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1,
+                                             uint32_t b2, uint32_t b3) {
+    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3) : "memory");
+}
 // {lo, hi} -> packed fp16 pair, round to nearest; the relu form clamps negative inputs to +0 in the same instruction
 __device__ __forceinline__ uint32_t cvt_pack_f16(float lo, float hi) {
     uint32_t d;
