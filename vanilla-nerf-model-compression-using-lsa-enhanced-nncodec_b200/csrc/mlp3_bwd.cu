@@ -61,7 +61,7 @@ template <bool kTrace>
 __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __grid_constant__ Bwd3Params prm) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t sbase = smem_u32(smem);
+    const uint32_t sbase = opaque_u32(smem_u32(smem));
     const int warp = uniform_warp_idx();
     const int lane = threadIdx.x & 31;
     auto bar = [&](int i) { return sbase + kS3Bars + 8u * i; };
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
         const int q = warp & 3, team = e >> 3, ph = (e >> 2) & 1;
         const uint32_t tmem_lane = tmem_base + (uint32_t(q * 32) << 16) + team * 256 + ph * 128;
         const uint32_t act = sbase + kS3Act;
-        const uint32_t pg_a = sbase + kS3BwdPg, ga_a = sbase + kS3BwdGa, max_a = sbase + kS3BwdMax;
+        const uint32_t pg_a = sbase + kS3BwdPg, ga_a = opaque_u32(sbase + kS3BwdGa + 4 * (ph * 128)), max_a = sbase + kS3BwdMax;
         const float2* g_sb = reinterpret_cast<const float2*>(prm.packed + kOffSB);
         const float* g_wa = reinterpret_cast<const float*>(prm.packed + kOffWAlpha);
         const float* g_wr = reinterpret_cast<const float*>(prm.packed + kOffWRgb);
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 const float ea = __ldg(&g_sb[kChAlpha]).x;
                 st_shared_v4(pg_a + 16 * pt, __float_as_uint(dr.x * rscale * er), __float_as_uint(dr.y * rscale * eg),
                              __float_as_uint(dr.z * rscale * eb), 0u);
-                st_shared_f32(ga_a + 4 * pt, dr.w * rscale * ea);
+                st_shared_f32(sbase + kS3BwdGa + 4 * pt, dr.w * rscale * ea);
             }
             if (e == 8 && lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(max_a + 4 * ((it & 1) ^ 1)), "r"(0u) : "memory");
             named_bar_sync3(1, 32 * kEpiWarps3);
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 const float2 c = __ldg(&g_sb[kChViews + chh]);
                 const float w0 = __ldg(&g_wr[chh]), w1 = __ldg(&g_wr[128 + chh]), w2 = __ldg(&g_wr[256 + chh]);
                 const uint8_t* hrow = saved_row(g, 9, chh);
-                const uint32_t row_addr = act + (chh >> 3) * kKGroup3 + (2 * ph) * kNGroup3 + (chh & 7u) * 128u;
+                const uint32_t row_addr = opaque_u32(act + (chh >> 3) * kKGroup3 + (2 * ph) * kNGroup3 + (chh & 7u) * 128u);
                 const uint32_t swz = (chh & 7u) << 4;
                 prefetch_slice(slice_ptr(g, 2));
                 float s1 = 0.0f, s2 = 0.0f;
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 const float2 c = c_next;
                 const float wa = (f & JB_ADD_ALPHA) ? __ldg(&g_wa[chh]) : 0.0f;
                 const uint8_t* hrow = saved_row(g, jb.slot, chh);
-                const uint32_t row_addr = act + (chh >> 3) * kKGroup3 + (2 * ph) * kNGroup3 + (chh & 7u) * 128u;
+                const uint32_t row_addr = opaque_u32(act + (chh >> 3) * kKGroup3 + (2 * ph) * kNGroup3 + (chh & 7u) * 128u);
                 const uint32_t swz = (chh & 7u) << 4;
                 // saved activations: two chunks are requested before the accumulator is waited for, then each consumed
                 // slot is refilled with the chunk two ahead
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                     if (f & JB_ADD_ALPHA) {        // d h8 also receives the alpha head's gradient
 #pragma unroll
                         for (int i = 0; i < 16; i += 4) {
-                            const float4 ga = ld_shared_v4f(ga_a + 4 * (ph * 128 + cc * 16 + i));
+                            const float4 ga = ld_shared_v4f(ga_a + 4 * (cc * 16 + i));
                             d[i] = fmaf(ga.x, wa, d[i]);
                             d[i + 1] = fmaf(ga.y, wa, d[i + 1]);
                             d[i + 2] = fmaf(ga.z, wa, d[i + 2]);

@@ -42,7 +42,7 @@ template <bool kSave, bool kTrace>
 __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid_constant__ Fwd3Params prm) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t sbase = smem_u32(smem);
+    const uint32_t sbase = opaque_u32(smem_u32(smem));
     const int warp = uniform_warp_idx();
     const int lane = threadIdx.x & 31;
     float* out_s = reinterpret_cast<float*>(smem + kS3Misc);
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                 // ---- 4 chunks of 16 points: TMEM -> y = acc*es + b -> (ReLU) -> fp16 -> operand tile ----
                 // The load of chunk i+1 is in flight while chunk i is converted and stored.
                 const bool relu = f & JB_RELU;
-                const uint32_t row_addr = act + (ch >> 3) * kKGroup3 + pq * kNGroup3 + (ch & 7u) * 128u;
+                const uint32_t row_addr = opaque_u32(act + (ch >> 3) * kKGroup3 + pq * kNGroup3 + (ch & 7u) * 128u);
                 const uint32_t swz = (ch & 7u) << 4;
                 uint8_t* save_ch = kSave ? save_g + (size_t)jb.slot * kSave3SlotBytes + save3_offset(0, ch) : nullptr;
                 uint32_t va[16], vb[16];

@@ -17,6 +17,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Identity the compiler cannot see through: keeps a derived address in a register instead of re-deriving it
+// (the aligned dynamic shared-memory base costs ~10 instructions to rebuild and ptxas rematerialises it freely).
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------
