@@ -32,6 +32,8 @@ QP, QP_DENSITY, NONWEIGHT_QP = -20, 2, -75
 FLOP_PER_POINT_FWD = 2 * 593408
 FLOP_PER_POINT_BWD = 2 * 557696
 METRIC = "rays/sec render_rays (64+128 samples/ray); LSA steps/sec"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 4096 rays x 192 samples (profiles/)
+NCU_DRAM_BYTES = {"mlp_bwd_fine": None, "mlp_fwd_fine": None}
 
 
 def synth_batch(n, seed, device="cpu"):
@@ -178,7 +180,7 @@ def run_cuda(args):
     for name, prm in wrapper.named_parameters():
         prm.requires_grad_(name.endswith("weight_scaling"))
     params = [q for q in wrapper.parameters() if q.requires_grad]
-    opt = torch.optim.Adam(params, lr=1e-4)
+    opt = torch.optim.Adam(params, lr=1e-4, fused=True)          # same update rule, one launch for the 24 scale tensors
     train_kw, _ = R.create_nerf(wrapper, perturb=1.0, white_bkgd=True, dataset_type="blender")
     R.DATA_PARALLEL["enabled"] = world > 1
 
@@ -303,17 +305,23 @@ def run_cuda(args):
             rows = {k: {"ms": v[0], "tflops": v[1] / (v[0] * 1e-3) / 1e12} for k, v in kern.items()}
             step_kernel_ms = sum(rows[k]["ms"] for k in ("mlp_fwd_coarse", "mlp_fwd_fine", "mlp_bwd_coarse", "mlp_bwd_fine"))
             dom = max(("mlp_fwd_fine", "mlp_bwd_fine"), key=lambda k: rows[k]["ms"])
-            line["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": rows[dom]["tflops"], "peak": pk["tensor"], "unit": "TFLOP/s",
-                                "frac": rows[dom]["tflops"] / pk["tensor"], "traffic": None, "peak_source": pk["source"] + " (sustained bf16)",
+            # the kernels are timed alone (10 back-to-back launches), so the denominator is the BURST bf16 figure;
+            # `traffic` = dram__bytes_read+write of one launch of this kernel from the committed ncu --set full capture
+            # (profiles/r01_ncu_mlp_kernels_summary.txt), not a live measurement
+            line["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": rows[dom]["tflops"], "peak": pk["tensor_burst"], "unit": "TFLOP/s",
+                                "frac": rows[dom]["tflops"] / pk["tensor_burst"], "traffic": NCU_DRAM_BYTES.get(dom),
+                                "peak_source": pk["source"] + " (burst bf16: kernel timed alone)",
+                                "frac_of_sustained": rows[dom]["tflops"] / pk["tensor"],
+                                "algorithmic_flop_per_launch": kern[dom][1],
                                 "share_of_step": rows[dom]["ms"] / ms_norequant, "mlp_kernels_share_of_step": step_kernel_ms / ms_norequant}
             line["kernels"] = rows
             # CPU baseline: the oracle port on this box's host cores, bounded sample
             try:
                 torch.set_num_threads(os.cpu_count() or 1)
-                sample = 256
-                sec, threads = cpu_lsa_steps(oracle_model(), sample, 2, 1)
+                sample = 1024
+                sec, threads = cpu_lsa_steps(oracle_model(), sample, 3, 1)
                 line["cpu_baseline"] = {"value": sample / sec, "unit": "rays/s", "cores": threads, "kind": "port",
-                                        "sample": f"{sample}-ray LSA steps (fwd+bwd+Adam) of the oracle, torch CPU fp32, mean of 2 after 1 warm-up"}
+                                        "sample": f"{sample}-ray LSA steps (fwd+bwd+Adam) of the oracle, torch CPU fp32, mean of 3 after 1 warm-up"}
             except Exception as ex:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": "rays/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
         print(json.dumps(line))
