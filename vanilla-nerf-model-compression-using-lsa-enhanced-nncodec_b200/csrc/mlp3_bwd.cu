@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
     {
         if (threadIdx.x < 2) reinterpret_cast<uint32_t*>(smem + kS3BwdMax)[threadIdx.x] = 0u;
     }
-    const uint32_t tmem_base = setup3(smem, sbase, warp, kEpiWarps3 / 2);      // each half has its own team of 8 warps
+    const uint32_t tmem_base = setup3(smem, sbase, warp);
     const int first = blockIdx.x, stride = gridDim.x;
     const int n_iters = first < prm.n_groups ? (prm.n_groups - first + stride - 1) / stride : 0;
 
@@ -84,19 +84,19 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
         // ================= epilogue warps =================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 " NERFQ_REGS_EPI3 ";");
         const int e = warp - kCtrlWarps3;
-        // Two teams of 8 warps: team 0 runs the jobs of channels 0..127 (and the views-layer job), team 1 those of
-        // channels 128..255, so the two jobs of a step overlap instead of queueing behind each other.  Within a team a
-        // warp owns lane quarter q and 128 points (ph).
-        const int q = warp & 3, team = e >> 3, ph = (e >> 2) & 1;
-        const uint32_t tmem_lane = tmem_base + (uint32_t(q * 32) << 16) + team * 256 + ph * 128;
+        // All 16 warps work on one job at a time (a job is latency- not issue-bound, so halving the points per warp
+        // halves its duration; two 8-warp teams running both jobs of a step concurrently measured slower).  A warp owns
+        // lane quarter q and point quarter pq (64 points = 4 chunks of 16) of both accumulators.
+        const int q = warp & 3, pq = e >> 2;
+        const uint32_t tmem_lane = tmem_base + (uint32_t(q * 32) << 16) + pq * 64;
         const uint32_t act = sbase + kS3Act;
-        const uint32_t pg_a = sbase + kS3BwdPg, ga_a = opaque_u32(sbase + kS3BwdGa + 4 * (ph * 128)), max_a = sbase + kS3BwdMax;
+        const uint32_t pg_a = sbase + kS3BwdPg, ga_a = opaque_u32(sbase + kS3BwdGa + 4 * (pq * 64)), max_a = sbase + kS3BwdMax;
         const float2* g_sb = reinterpret_cast<const float2*>(prm.packed + kOffSB);
         const float* g_wa = reinterpret_cast<const float*>(prm.packed + kOffWAlpha);
         const float* g_wr = reinterpret_cast<const float*>(prm.packed + kOffWRgb);
-        uint32_t ph_acc = 0, ph_sf = 0;
+        uint32_t ph_acc0 = 0, ph_acc1 = 0, ph_sf = 0;
         unsigned long long t_pro = 0, t_acc = 0, t_job = 0, t_views = 0;
-        const bool tracing = kTrace && lane == 0 && (e == 1 || e == 9);
+        const bool tracing = kTrace && lane == 0 && e == 5;
         const int cl = 32 * q + lane;                 // this thread's channel within a half (its TMEM lane)
 
         auto publish = [&](int which) {
@@ -105,16 +105,16 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(which));
         };
-        // saved activations of this thread: channel chh of slot `slot`, its 8 chunks of 16 points start at point chunk 8*ph
+        // saved activations of this thread: channel chh of slot `slot`, its 4 chunks of 16 points start at point chunk 4*pq
         auto saved_row = [&](int g, int slot, uint32_t chh) {
-            return prm.save + (size_t)g * kSave3GroupBytes + (size_t)slot * kSave3SlotBytes + save3_offset(8 * ph, chh);
+            return prm.save + (size_t)g * kSave3GroupBytes + (size_t)slot * kSave3SlotBytes + save3_offset(4 * pq, chh);
         };
         // one chunk of 16 points of this thread's channel.  d = gradient w.r.t. the layer output (fp32, from TMEM),
         // h = saved activations (8 x half2).  The elementwise work runs on packed halves:
         //   dh = fp16(d);  s1h += dh*h;  g = dh*es (masked where the unit was inactive);  s2h += g;  G row <- g
         // The half2 partial sums cover 8 terms each and are folded into the fp32 sums per chunk (rounding errors are
         // unbiased and average out over the ~10^5 chunks a channel sees).
-        auto chunk16 = [&](const float (&d)[16], const uint4 h0, const uint4 h1, __half2 es2, bool relu, bool write, uint32_t row_addr,
+        auto chunk16 = [&](const uint32_t (&dpk)[8], const uint4 h0, const uint4 h1, __half2 es2, bool relu, bool write, uint32_t row_addr,
                            uint32_t swz, int cc, float& s1, float& s2) {
             const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
             uint32_t pk[8];
@@ -123,8 +123,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const __half2 h2 = *reinterpret_cast<const __half2*>(&hw[i]);
-                const uint32_t dw = cvt_pack_f16(d[2 * i], d[2 * i + 1]);
-                const __half2 dh = *reinterpret_cast<const __half2*>(&dw);
+                const __half2 dh = *reinterpret_cast<const __half2*>(&dpk[i]);
                 s1h = __hfma2(dh, h2, s1h);
                 __half2 g2 = __hmul2(dh, es2);
                 if (relu) g2 = __hmul2(g2, __hgt2(h2, zero2));       // mask: 1.0 where the unit was active
@@ -137,33 +136,28 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
             if (write) {
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
-                    st_shared_v4(row_addr + (cc >> 2) * kNGroup3 + ((uint32_t)(((cc & 3) * 2 + k) << 4) ^ swz), pk[4 * k], pk[4 * k + 1],
-                                 pk[4 * k + 2], pk[4 * k + 3]);
+                    st_shared_v4(row_addr + ((uint32_t)((cc * 2 + k) << 4) ^ swz), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
             }
         };
-        // chunk cc (0..7) of this thread's 128 points: 32 bytes, 8 KB apart (mlp3_layout.h, save3_offset)
+        // chunk cc (0..3) of this thread's 64 points: 32 bytes, 8 KB apart (mlp3_layout.h, save3_offset)
         auto pair_off = [&](int cc, uint32_t) { return save3_offset(cc, 0); };
-        // 64 KB slice of saved activations read by this team's i-th job of group g.  Team 0: views job (i = 0), then
-        // jobs 0, 2, .., 16; team 1: jobs 1, 3, .., 17.  i past the end continues in the CTA's next group.
-        const int team_jobs = team == 0 ? kBwd3Jobs / 2 + 1 : kBwd3Jobs / 2;
-        auto slice_ptr = [&](int g, int i) -> const uint8_t* {
-            if (i >= team_jobs) { i -= team_jobs; g += stride; }
+        // 64 KB slice of saved activations read by job v of group g (v = -1: the views-layer job; v >= kBwd3Jobs: the
+        // CTA's next group, starting with its views job)
+        auto slice_ptr = [&](int g, int v) -> const uint8_t* {
+            if (v >= kBwd3Jobs) { v -= kBwd3Jobs + 1; g += stride; }
             if (g >= prm.n_groups) g = prm.n_groups - 1;
             const uint8_t* base = prm.save + (size_t)g * kSave3GroupBytes;
-            if (team == 0 && i == 0) return base + (size_t)9 * kSave3SlotBytes;
-            const Job3 jn = prm.prog.job[team == 0 ? 2 * (i - 1) : 2 * i + 1];
+            if (v < 0) return base + (size_t)9 * kSave3SlotBytes;
+            const Job3 jn = prm.prog.job[v];
             return base + (size_t)jn.slot * kSave3SlotBytes + ((jn.flags & JB_HI_HALF) ? save3_offset(0, 128) : 0);
         };
-        const int tl = (e & 7) * 32 + lane;        // thread index within the team: prefetches lines tl and tl + 256
-        // a job's 64 KB are 16 pieces of 4 KB (128 channels x 32 B), one per point chunk, 8 KB apart: 32 lines each
-        auto prefetch_slice = [&](const uint8_t* sl) {
-            prefetch_l2_line(sl + (tl >> 5) * 8192 + (tl & 31) * 128);
-            prefetch_l2_line(sl + ((tl + 256) >> 5) * 8192 + (tl & 31) * 128);
-        };
+        // a job's 64 KB are 16 pieces of 4 KB (128 channels x 32 B), one per point chunk, 8 KB apart: 512 lines, one per thread
+        const int tl = e * 32 + lane;
+        auto prefetch_slice = [&](const uint8_t* sl) { prefetch_l2_line(sl + (tl >> 5) * 8192 + (tl & 31) * 128); };
         float2 c_next = make_float2(1.f, 0.f);
         if (n_iters > 0) {
-            if (team == 1) publish(kB3ActHi);       // D_hi is free at kernel start
-            c_next = __ldg(&g_sb[prm.prog.job[team].ch + cl]);
+            publish(kB3ActHi);       // D_hi is free at kernel start
+            c_next = __ldg(&g_sb[prm.prog.job[0].ch + cl]);
         }
         int it = 0;
         for (int g = first; g < prm.n_groups; g += stride, ++it) {
@@ -178,6 +172,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 rw = *reinterpret_cast<const float4*>(prm.raw + 4 * gidx);
             }
             if (it == 0) {         // later groups: prefetched by the previous group's last jobs
+                prefetch_slice(slice_ptr(g, -1));
                 prefetch_slice(slice_ptr(g, 0));
                 prefetch_slice(slice_ptr(g, 1));
             }
@@ -227,92 +222,99 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
             if (e == 8 && lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(max_a + 4 * ((it & 1) ^ 1)), "r"(0u) : "memory");
             named_bar_sync3(1, 32 * kEpiWarps3);
 
-            // ---- views-layer job (team 0): d hv[k][n] = sum_c g_c[n] * w_rgb[c][k], channels 0..127 ----
+            // ---- views-layer job: d hv[k][n] = sum_c g_c[n] * w_rgb[c][k], channels 0..127 ----
             if (tracing) { const unsigned long long t = clock64(); t_pro += t - tp0; tp0 = t; }
-            if (team == 0) {
+            {
                 const uint32_t chh = cl;                                   // views hidden channel
                 const float2 c = __ldg(&g_sb[kChViews + chh]);
                 const float w0 = __ldg(&g_wr[chh]), w1 = __ldg(&g_wr[128 + chh]), w2 = __ldg(&g_wr[256 + chh]);
                 const uint8_t* hrow = saved_row(g, 9, chh);
-                const uint32_t row_addr = opaque_u32(act + (chh >> 3) * kKGroup3 + (2 * ph) * kNGroup3 + (chh & 7u) * 128u);
+                const uint32_t row_addr = opaque_u32(act + (chh >> 3) * kKGroup3 + pq * kNGroup3 + (chh & 7u) * 128u);
                 const uint32_t swz = (chh & 7u) << 4;
-                prefetch_slice(slice_ptr(g, 2));
                 float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll 1
-                for (int cc = 0; cc < 8; ++cc) {
+                for (int cc = 0; cc < 4; ++cc) {
                     const H32 hp = ldg_nc_32B(hrow + pair_off(cc, swz));
                     float d[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float4 gq = ld_shared_v4f(pg_a + 16 * (ph * 128 + cc * 16 + i));
+                        const float4 gq = ld_shared_v4f(pg_a + 16 * (pq * 64 + cc * 16 + i));
                         d[i] = fmaf(gq.x, w0, fmaf(gq.y, w1, gq.z * w2));
                     }
-                    chunk16(d, hp.a, hp.b, __float2half2_rn(c.x), true, true, row_addr, swz, cc, s1, s2);
+                    uint32_t dpk[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dpk[i] = cvt_pack_f16(d[2 * i], d[2 * i + 1]);
+                    chunk16(dpk, hp.a, hp.b, __float2half2_rn(c.x), true, true, row_addr, swz, cc, s1, s2);
                 }
                 // ds * s = sum dY (y - b) = s1 - b * (sum dY);  s2 accumulated dY*es
                 publish(kB3ActLo);
                 red_global_add_f32(prm.grad_tmp + kChViews + chh, (s1 - c.y * (s2 / c.x)) * rinv);
             }
 
-            // ================= dgrad chain: this team's jobs =================
+            // ================= dgrad chain =================
             if (tracing) t_views += clock64() - tp0;
 #pragma unroll 1
-            for (int j = team; j < kBwd3Jobs; j += 2) {
+            for (int j = 0; j < kBwd3Jobs; ++j) {
                 const Job3 jb = prm.prog.job[j];
                 const uint32_t f = jb.flags;
-                const uint32_t chh = 128u * team + cl;                     // channel within the layer
+                const uint32_t hi = (f & JB_HI_HALF) ? 1u : 0u;
+                const uint32_t chh = 128u * hi + cl;                       // channel within the layer
                 const float2 c = c_next;
                 const float wa = (f & JB_ADD_ALPHA) ? __ldg(&g_wa[chh]) : 0.0f;
                 const uint8_t* hrow = saved_row(g, jb.slot, chh);
-                const uint32_t row_addr = opaque_u32(act + (chh >> 3) * kKGroup3 + (2 * ph) * kNGroup3 + (chh & 7u) * 128u);
+                const uint32_t row_addr = opaque_u32(act + (chh >> 3) * kKGroup3 + pq * kNGroup3 + (chh & 7u) * 128u);
                 const uint32_t swz = (chh & 7u) << 4;
                 // saved activations: two chunks are requested before the accumulator is waited for, then each consumed
                 // slot is refilled with the chunk two ahead
                 H32 hh[2];
                 hh[0] = ldg_nc_32B(hrow + pair_off(0, swz));
                 hh[1] = ldg_nc_32B(hrow + pair_off(1, swz));
-                // L2 prefetch of the slice this team needs two jobs from now (512 lines, two per thread)
-                prefetch_slice(slice_ptr(g, (team == 0 ? j / 2 + 1 : j / 2) + 2));
+                prefetch_slice(slice_ptr(g, j + 2));          // the job after next, into L2 (one line per thread)
+                if (j + 2 == kBwd3Jobs + 1) prefetch_slice(slice_ptr(g, j + 3));
                 unsigned long long tj0 = 0;
                 if (tracing) tj0 = clock64();
-                mbar_wait(bar(kB3AccReady + team), ph_acc);
-                ph_acc ^= 1;
+                if (hi) { mbar_wait(bar(kB3AccReady + 1), ph_acc1); ph_acc1 ^= 1; }
+                else { mbar_wait(bar(kB3AccReady + 0), ph_acc0); ph_acc0 ^= 1; }
                 tc_fence_after_sync();
                 if (tracing) { const unsigned long long t = clock64(); t_acc += t - tj0; tj0 = t; }
-                c_next = __ldg(&g_sb[prm.prog.job[j + 2 < kBwd3Jobs ? j + 2 : team].ch + cl]);        // in flight during this job
+                c_next = __ldg(&g_sb[prm.prog.job[j + 1 < kBwd3Jobs ? j + 1 : 0].ch + cl]);        // in flight during this job
+                const uint32_t ta = tmem_lane + (hi ? 256u : 0u);
                 const bool relu = f & JB_RELU, write = !(f & JB_NO_WRITE);
                 const __half2 es2 = __float2half2_rn(c.x);
                 float s1 = 0.0f, s2 = 0.0f;
+                uint32_t va[16];
+                tmem_ld16(ta, va);
 #pragma unroll
-                for (int cc = 0; cc < 8; ++cc) {
-                    uint32_t va[16];
-                    tmem_ld16(tmem_lane + 16 * cc, va);
+                for (int cc = 0; cc < 4; ++cc) {
                     tmem_ld_wait();
-                    float d[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) d[i] = __uint_as_float(va[i]);
                     if (f & JB_ADD_ALPHA) {        // d h8 also receives the alpha head's gradient
 #pragma unroll
                         for (int i = 0; i < 16; i += 4) {
                             const float4 ga = ld_shared_v4f(ga_a + 4 * (cc * 16 + i));
-                            d[i] = fmaf(ga.x, wa, d[i]);
-                            d[i + 1] = fmaf(ga.y, wa, d[i + 1]);
-                            d[i + 2] = fmaf(ga.z, wa, d[i + 2]);
-                            d[i + 3] = fmaf(ga.w, wa, d[i + 3]);
+                            va[i] = __float_as_uint(fmaf(ga.x, wa, __uint_as_float(va[i])));
+                            va[i + 1] = __float_as_uint(fmaf(ga.y, wa, __uint_as_float(va[i + 1])));
+                            va[i + 2] = __float_as_uint(fmaf(ga.z, wa, __uint_as_float(va[i + 2])));
+                            va[i + 3] = __float_as_uint(fmaf(ga.w, wa, __uint_as_float(va[i + 3])));
                         }
                     }
+                    // fp16 copy of the gradients; the accumulator registers are then free for the next chunk's load,
+                    // which is in flight while this chunk is processed
+                    uint32_t dpk[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dpk[i] = cvt_pack_f16(__uint_as_float(va[2 * i]), __uint_as_float(va[2 * i + 1]));
+                    if (cc < 3) tmem_ld16(ta + 16 * (cc + 1), va);
                     if (cc == 0 && (f & JB_WAIT_SF)) { mbar_wait(bar(kB3StageFree + (q >> 1)), ph_sf); ph_sf ^= 1; }
                     const H32 hp = hh[cc & 1];
-                    if (cc < 6) hh[cc & 1] = ldg_nc_32B(hrow + pair_off(cc + 2, swz));       // refill with chunk cc + 2
-                    chunk16(d, hp.a, hp.b, es2, relu, write, row_addr, swz, cc, s1, s2);
+                    if (cc < 2) hh[cc & 1] = ldg_nc_32B(hrow + pair_off(cc + 2, swz));       // refill with chunk cc + 2
+                    chunk16(dpk, hp.a, hp.b, es2, relu, write, row_addr, swz, cc, s1, s2);
                 }
-                if (write || team) publish(team ? kB3ActHi : kB3ActLo);
+                if (write || hi) publish(hi ? kB3ActHi : kB3ActLo);
                 red_global_add_f32(prm.grad_tmp + jb.ch + cl, (s1 - c.y * (s2 / c.x)) * rinv);     // after the hand-over
                 if (tracing) t_job += clock64() - tj0;
             }
         }
         if (tracing && prm.dbg) {
-            unsigned long long* o = prm.dbg + 8 * 148 + 32 * blockIdx.x + 8 * team;
+            unsigned long long* o = prm.dbg + 8 * 148 + 32 * blockIdx.x;
             o[0] = t_pro; o[1] = t_views; o[2] = t_acc; o[3] = t_job;
         }
     }
