@@ -174,14 +174,10 @@ def run_cuda(args):
     import nerfq_b200  # noqa: F401
     from nerfq_b200 import codec, model as nmodel, ops, packed, render as R
 
+    from nerfq_b200 import lsa
     torch.manual_seed(0)
     wrapper = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params().to(dev)
     master = {k: v.detach().clone() for k, v in wrapper.state_dict().items()}      # unquantised float weights
-    for name, prm in wrapper.named_parameters():
-        prm.requires_grad_(name.endswith("weight_scaling"))
-    params = [q for q in wrapper.parameters() if q.requires_grad]
-    opt = torch.optim.Adam(params, lr=1e-4, fused=True)          # same update rule, one launch for the 24 scale tensors
-    train_kw, _ = R.create_nerf(wrapper, perturb=1.0, white_bkgd=True, dataset_type="blender")
     R.DATA_PARALLEL["enabled"] = world > 1
 
     o_h, d_h, t_h = synth_batch(RAYS_PER_GPU, 2 + 10 * rank)
@@ -189,29 +185,24 @@ def run_cuda(args):
     t_h = t_h.pin_memory()
     rays_d = rays_h.to(dev)
     t_d = t_h.to(dev)
-    sd0 = wrapper.state_dict()
-    restore_keys = [k for k in master if k.endswith(".weight") or k.endswith(".bias")]
-    restore_dst = [sd0[k] for k in restore_keys]
-    restore_src = [master[k] for k in restore_keys]
-
-    def requantize():
-        """BASELINE cfg2 'quantize' leg: float weights -> levels at qp (GPU kernel), repacked for the MLP."""
-        with torch.no_grad():
-            torch._foreach_copy_(restore_dst, restore_src)          # the unquantised float weights and biases
-        codec.quantize_model(wrapper, QP, QP_DENSITY, NONWEIGHT_QP)
-
-    def lsa_step(rays, target, requant):
-        if requant:
-            requantize()
-        rgb, disp, acc, extras = R.render(4, 4, None, chunk=32768, rays=rays, near=2.0, far=6.0, retraw=False, **train_kw)
-        loss = R.img2mse(rgb, target) + R.img2mse(extras["rgb0"], target)
-        loss.backward()
-        opt.step()
-        opt.zero_grad(set_to_none=True)
-        return loss
-
+    # BASELINE cfg2 'quantize' leg: float weights -> levels at qp (GPU kernel), repacked for the MLP
+    requantize = lsa.make_requantizer(wrapper, master, QP, QP_DENSITY, NONWEIGHT_QP)
     requantize()
     requant_each_step = not args.no_requant
+    # the public API a user calls per iteration (nerfq_b200.lsa.LSAStep); the iteration is captured in a CUDA graph
+    # unless --eager is given (or capture fails: recorded in config.cuda_graph)
+    step_kw = dict(lr=1e-4, perturb=1.0, white_bkgd=True, dataset_type="blender")
+    step_main = lsa.LSAStep(wrapper, RAYS_PER_GPU, requantize=requantize if requant_each_step else None, **step_kw)
+    step_noq = lsa.LSAStep(wrapper, RAYS_PER_GPU, requantize=None, **step_kw)
+    graphed = False
+    if not args.eager and (world == 1 or os.environ.get("NERFQ_GRAPH_DP", "1") == "1"):
+        try:
+            step_main.capture()
+            step_noq.capture()
+            graphed = True
+        except Exception as ex:  # noqa: BLE001
+            sys.stderr.write(f"CUDA graph capture failed, running eagerly: {ex}\n")
+            step_main.graph = step_noq.graph = None
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -237,16 +228,13 @@ def run_cuda(args):
     if rank == 0:
         sampler.start()
     # (1) device-resident inputs
-    ms_step = timed(lambda: lsa_step((rays_d[0], rays_d[1]), t_d, requant_each_step), args.steps, args.warmup)
+    ms_step = timed(lambda: step_main(rays_d, t_d), args.steps, args.warmup)
     # (2) end to end through the public API with host buffers: H2D of rays+target, D2H of the loss, every step
     def e2e_step():
-        r = rays_h.to(dev, non_blocking=True)
-        t = t_h.to(dev, non_blocking=True)
-        loss = lsa_step((r[0], r[1]), t, requant_each_step)
-        return float(loss.detach().cpu())
+        return float(step_main(rays_h, t_h).cpu())          # pinned host rays + target in, loss out, every step
     ms_e2e = timed(e2e_step, args.steps, min(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
-    ms_norequant = timed(lambda: lsa_step((rays_d[0], rays_d[1]), t_d, False), args.steps, 3)
+    ms_norequant = timed(lambda: step_noq(rays_d, t_d), args.steps, 3)
 
     # (3) forward-only rendering (test-view path): rays/s through render_rays without saving activations
     _, test_kw = R.create_nerf(wrapper, white_bkgd=True, dataset_type="blender")
@@ -289,7 +277,7 @@ def run_cuda(args):
                 "config": {"workload": "cfg2: LSA fine-tuning step at qp=-20 (quantise -> LSA-scaled dequant in the MLP epilogue -> "
                                        "render 4096 rays/GPU, 64+128 samples -> backward into LSA scales -> Adam)",
                            "rays_per_gpu": RAYS_PER_GPU, "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE, "qp": QP,
-                           "perturb": 1.0, "white_bkgd": True, "requantize_every_step": requant_each_step,
+                           "perturb": 1.0, "white_bkgd": True, "requantize_every_step": requant_each_step, "cuda_graph": graphed,
                            "operands": "fp16 operands, fp32 accumulate (TMEM)",
                            "parallelism": f"dp{world}" if world > 1 else "single",
                            "l2": "per-step working set (saved activations 5.1 GB/GPU) exceeds the 126 MB L2; no explicit flush"},
@@ -336,6 +324,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-requant", action="store_true", help="quantise once before the loop (what the reference does)")
+    ap.add_argument("--eager", action="store_true", help="do not capture the LSA iteration in a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -46,6 +46,12 @@ buf = torch.zeros(148 * 8 + 148 * 32, dtype=torch.int64, device=dev)
 L.nerfq_mlp_set_trace_bwd(buf.data_ptr())
 ops.mlp_backward(pn, d_raw, raw, save, acc)
 torch.cuda.synchronize()
+e0.record()
+for _ in range(5):
+    ops.mlp_backward(pn, d_raw, raw, save, acc)
+e1.record()
+torch.cuda.synchronize()
+print(f"bwd (tracing variant) {e0.elapsed_time(e1) / 5:.3f} ms")
 L.nerfq_mlp_set_trace_bwd(None)
 groups = (n * S // 256 + 147) // 148
 t = buf.cpu().numpy()[:148 * 8].reshape(148, 8).astype(np.float64).mean(0) / groups

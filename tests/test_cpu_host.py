@@ -136,3 +136,17 @@ def test_two_rank_gloo(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0, out
+
+
+def test_lsa_parameter_selection_matches_tune_model():
+    """lsa.lsa_parameters mirrors tune_model(lsa_flag=True, ft_flag=False): only the 24 weight_scaling tensors train
+    (framework/pytorch_model/__init__.py:1131-1145); LSAStep refuses a CPU model instead of falling back."""
+    import pytest
+    from nerfq_b200 import lsa, model as nmodel
+    w = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params()
+    params = lsa.lsa_parameters(w)
+    assert len(params) == 24
+    trainable = [n for n, p in w.named_parameters() if p.requires_grad]
+    assert len(trainable) == 24 and all(n.endswith("weight_scaling") for n in trainable)
+    with pytest.raises(RuntimeError):
+        lsa.LSAStep(w, 16)

@@ -78,3 +78,43 @@ def test_lsa_step_oracle_larger(dev):
     before = params[0].detach().clone()
     torch.optim.Adam(params, lr=1e-4).step()
     assert not torch.equal(before, params[0].detach())
+
+
+def test_lsa_step_graph_replay_matches_eager(dev):
+    """nerfq_b200.lsa.LSAStep: three iterations replayed from the captured CUDA graph (perturb=0, requantise every
+    step) follow three eager iterations from the same start: same losses, same scale gradients (up to the summation
+    order of the float atomics), bit-identical integer levels.  The scales themselves are compared by their median
+    deviation: Adam divides by |g| + 1e-8, so for the few elements with |g| ~ 1e-9 the atomics' summation-order noise
+    (~1e-9 absolute) shows up as a fraction of lr."""
+    import copy
+    from nerfq_b200 import lsa, model as nmodel
+    torch.manual_seed(3)
+    base = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params().to(dev)
+    r = synth_rays(512, 5)
+    rays = torch.stack([r[:, :3], r[:, 3:6]], 0).contiguous().pin_memory()
+    target = torch.rand(512, 3, generator=torch.Generator().manual_seed(6)).pin_memory()
+    results = []
+    for graph in (False, True):
+        w = copy.deepcopy(base)
+        master = {k: v.detach().clone() for k, v in w.state_dict().items()}
+        rq = lsa.make_requantizer(w, master, -20)
+        rq()
+        step = lsa.LSAStep(w, 512, lr=1e-3, requantize=rq, perturb=0.0, white_bkgd=True)
+        if graph:
+            step.capture(warmup=0)
+            assert step.graph is not None
+        losses, first_grads = [], None
+        for i in range(3):
+            losses.append(float(step(rays, target).cpu()))
+            if i == 0:
+                first_grads = [p.grad.detach().clone() for p in step.params]
+        results.append((losses, first_grads, [p.detach().clone() for p in step.params], [l.clone() for l in w.model_fine.quant_levels]))
+    (l0, g0, p0, q0), (l1, g1, p1, q1) = results
+    assert np.allclose(l0, l1, rtol=1e-5, atol=1e-7), (l0, l1)
+    assert l0[2] != l0[0]                                  # the scales moved
+    for a, b in zip(g0, g1):
+        assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max()) + 1e-12
+    dev_all = torch.cat([(a - b).abs().reshape(-1) for a, b in zip(p0, p1)])
+    assert float(dev_all.median()) < 2e-6 and float(dev_all.max()) < 1e-3, (float(dev_all.median()), float(dev_all.max()))
+    for a, b in zip(q0, q1):
+        assert torch.equal(a, b)

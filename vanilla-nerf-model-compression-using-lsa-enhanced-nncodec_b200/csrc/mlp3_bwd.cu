@@ -36,8 +36,8 @@ struct Bwd3Params {
 };
 
 constexpr uint32_t kS3BwdGa = kS3BwdPg + 4096;          // float ga[256]: alpha-head gradient per point
-constexpr uint32_t kS3BwdMax = kS3BwdGa + 1024;         // uint gmax[2]
-static_assert(kS3BwdMax + 8 <= kS3Misc, "backward scratch must fit the encoding-tile region");
+constexpr uint32_t kS3BwdMax = kS3BwdGa + 1024;         // uint gmax[2], float rinv[2]
+static_assert(kS3BwdMax + 16 <= kS3Misc, "backward scratch must fit the encoding-tile region");
 
 // one 128-byte line into L2
 __device__ __forceinline__ void prefetch_l2_line(const void* p) {
@@ -69,7 +69,10 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
     {
         if (threadIdx.x < 2) reinterpret_cast<uint32_t*>(smem + kS3BwdMax)[threadIdx.x] = 0u;
     }
-    const uint32_t tmem_base = setup3(smem, sbase, warp);
+    // the CTA owns the SM (1 CTA/SM by shared-memory size) and allocates all 512 TMEM columns, so the allocation starts
+    // at column 0; treating the base as a constant frees a register in every epilogue thread
+    constexpr uint32_t tmem_base = 0;
+    if (setup3(smem, sbase, warp) != tmem_base) __trap();
     const int first = blockIdx.x, stride = gridDim.x;
     const int n_iters = first < prm.n_groups ? (prm.n_groups - first + stride - 1) / stride : 0;
 
@@ -83,14 +86,17 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
     } else {
         // ================= epilogue warps =================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 " NERFQ_REGS_EPI3 ";");
-        const int e = warp - kCtrlWarps3;
+        // the role dispatch above uses the shuffled (uniform-register) warp index; the per-thread geometry below is derived
+        // from threadIdx so that the compiler rematerialises it from the special register rather than spilling it
+        const int tw = (int)(threadIdx.x >> 5);
+        const int e = tw - kCtrlWarps3;
         // All 16 warps work on one job at a time (a job is latency- not issue-bound, so halving the points per warp
         // halves its duration; two 8-warp teams running both jobs of a step concurrently measured slower).  A warp owns
         // lane quarter q and point quarter pq (64 points = 4 chunks of 16) of both accumulators.
-        const int q = warp & 3, pq = e >> 2;
+        const int q = tw & 3, pq = e >> 2;
         const uint32_t tmem_lane = tmem_base + (uint32_t(q * 32) << 16) + pq * 64;
         const uint32_t act = sbase + kS3Act;
-        const uint32_t pg_a = sbase + kS3BwdPg, ga_a = opaque_u32(sbase + kS3BwdGa + 4 * (pq * 64)), max_a = sbase + kS3BwdMax;
+        const uint32_t pg_a = sbase + kS3BwdPg, ga_a = sbase + kS3BwdGa + 4 * (pq * 64), max_a = sbase + kS3BwdMax;
         const float2* g_sb = reinterpret_cast<const float2*>(prm.packed + kOffSB);
         const float* g_wa = reinterpret_cast<const float*>(prm.packed + kOffWAlpha);
         const float* g_wr = reinterpret_cast<const float*>(prm.packed + kOffWRgb);
@@ -111,10 +117,11 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
         };
         // one chunk of 16 points of this thread's channel.  d = gradient w.r.t. the layer output (fp32, from TMEM),
         // h = saved activations (8 x half2).  The elementwise work runs on packed halves:
-        //   dh = fp16(d);  s1h += dh*h;  g = dh*es (masked where the unit was inactive);  s2h += g;  G row <- g
+        //   dh = fp16(d);  s1h += dh*h;  g = dh (masked where the unit was inactive);  s2h += g;  G row <- g
+        // (the channel's delta*scale factor of the dgrad GEMM lives in the backward weight image, mlp3_layout.h)
         // The half2 partial sums cover 8 terms each and are folded into the fp32 sums per chunk (rounding errors are
         // unbiased and average out over the ~10^5 chunks a channel sees).
-        auto chunk16 = [&](const uint32_t (&dpk)[8], const uint4 h0, const uint4 h1, __half2 es2, bool relu, bool write, uint32_t row_addr,
+        auto chunk16 = [&](const uint32_t (&dpk)[8], const uint4 h0, const uint4 h1, bool relu, bool write, uint32_t row_addr,
                            uint32_t swz, int cc, float& s1, float& s2) {
             const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
             uint32_t pk[8];
@@ -125,8 +132,8 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 const __half2 h2 = *reinterpret_cast<const __half2*>(&hw[i]);
                 const __half2 dh = *reinterpret_cast<const __half2*>(&dpk[i]);
                 s1h = __hfma2(dh, h2, s1h);
-                __half2 g2 = __hmul2(dh, es2);
-                if (relu) g2 = __hmul2(g2, __hgt2(h2, zero2));       // mask: 1.0 where the unit was active
+                __half2 g2 = dh;
+                if (relu) g2 = __hmul2(dh, __hgt2(h2, zero2));       // mask: 1.0 where the unit was active
                 s2h = __hadd2(s2h, g2);
                 pk[i] = *reinterpret_cast<const uint32_t*>(&g2);
             }
@@ -141,19 +148,13 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
         };
         // chunk cc (0..3) of this thread's 64 points: 32 bytes, 8 KB apart (mlp3_layout.h, save3_offset)
         auto pair_off = [&](int cc, uint32_t) { return save3_offset(cc, 0); };
-        // 64 KB slice of saved activations read by job v of group g (v = -1: the views-layer job; v >= kBwd3Jobs: the
-        // CTA's next group, starting with its views job)
-        auto slice_ptr = [&](int g, int v) -> const uint8_t* {
-            if (v >= kBwd3Jobs) { v -= kBwd3Jobs + 1; g += stride; }
-            if (g >= prm.n_groups) g = prm.n_groups - 1;
-            const uint8_t* base = prm.save + (size_t)g * kSave3GroupBytes;
-            if (v < 0) return base + (size_t)9 * kSave3SlotBytes;
-            const Job3 jn = prm.prog.job[v];
-            return base + (size_t)jn.slot * kSave3SlotBytes + ((jn.flags & JB_HI_HALF) ? save3_offset(0, 128) : 0);
+        // L2 prefetch of the saved activations, three jobs ahead.  A job's 64 KB slice (mlp3_layout.h, Prog3Bwd::slice_off)
+        // is 16 pieces of 4 KB (128 channels x 32 B), one per point chunk, 8 KB apart: 512 lines, one per thread.
+        const uint32_t pf_thread = (uint32_t)e * 8192u + (uint32_t)lane * 128u;
+        auto prefetch_seq = [&](int g, int v) {      // v: index into [views, job 0 .. 17], may run over into the CTA's next group
+            if (v > kBwd3Jobs) { v -= kBwd3Jobs + 1; g = g + stride < prm.n_groups ? g + stride : g; }
+            prefetch_l2_line(prm.save + (size_t)g * kSave3GroupBytes + (pf_thread + prm.prog.slice_off[v]));
         };
-        // a job's 64 KB are 16 pieces of 4 KB (128 channels x 32 B), one per point chunk, 8 KB apart: 512 lines, one per thread
-        const int tl = e * 32 + lane;
-        auto prefetch_slice = [&](const uint8_t* sl) { prefetch_l2_line(sl + (tl >> 5) * 8192 + (tl & 31) * 128); };
         float2 c_next = make_float2(1.f, 0.f);
         if (n_iters > 0) {
             publish(kB3ActHi);       // D_hi is free at kernel start
@@ -172,9 +173,9 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 rw = *reinterpret_cast<const float4*>(prm.raw + 4 * gidx);
             }
             if (it == 0) {         // later groups: prefetched by the previous group's last jobs
-                prefetch_slice(slice_ptr(g, -1));
-                prefetch_slice(slice_ptr(g, 0));
-                prefetch_slice(slice_ptr(g, 1));
+                prefetch_seq(g, 0);
+                prefetch_seq(g, 1);
+                prefetch_seq(g, 2);
             }
             const uint32_t slot_max = max_a + 4 * (it & 1);
             if (e < 8) {
@@ -219,7 +220,13 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                              __float_as_uint(dr.z * rscale * eb), 0u);
                 st_shared_f32(sbase + kS3BwdGa + 4 * pt, dr.w * rscale * ea);
             }
-            if (e == 8 && lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(max_a + 4 * ((it & 1) ^ 1)), "r"(0u) : "memory");
+            // 1/scale is read back from shared memory where it is needed (once per job): a register would be spilled to
+            // local memory, whose loads take ~1000 cycles with the L1 carved out for shared memory
+            const uint32_t rinv_a = max_a + 8 + 4 * (it & 1);
+            if (e == 8 && lane == 0) {
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(max_a + 4 * ((it & 1) ^ 1)), "r"(0u) : "memory");
+                st_shared_f32(rinv_a, rinv);
+            }
             named_bar_sync3(1, 32 * kEpiWarps3);
 
             // ---- views-layer job: d hv[k][n] = sum_c g_c[n] * w_rgb[c][k], channels 0..127 ----
@@ -229,7 +236,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 const float2 c = __ldg(&g_sb[kChViews + chh]);
                 const float w0 = __ldg(&g_wr[chh]), w1 = __ldg(&g_wr[128 + chh]), w2 = __ldg(&g_wr[256 + chh]);
                 const uint8_t* hrow = saved_row(g, 9, chh);
-                const uint32_t row_addr = opaque_u32(act + (chh >> 3) * kKGroup3 + pq * kNGroup3 + (chh & 7u) * 128u);
+                const uint32_t row_addr = act + (chh >> 3) * kKGroup3 + pq * kNGroup3 + (chh & 7u) * 128u;
                 const uint32_t swz = (chh & 7u) << 4;
                 float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll 1
@@ -244,11 +251,11 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                     uint32_t dpk[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) dpk[i] = cvt_pack_f16(d[2 * i], d[2 * i + 1]);
-                    chunk16(dpk, hp.a, hp.b, __float2half2_rn(c.x), true, true, row_addr, swz, cc, s1, s2);
+                    chunk16(dpk, hp.a, hp.b, true, true, row_addr, swz, cc, s1, s2);
                 }
-                // ds * s = sum dY (y - b) = s1 - b * (sum dY);  s2 accumulated dY*es
+                // ds * s = sum dY (y - b) = s1 - b * (sum dY)
                 publish(kB3ActLo);
-                red_global_add_f32(prm.grad_tmp + kChViews + chh, (s1 - c.y * (s2 / c.x)) * rinv);
+                red_global_add_f32(prm.grad_tmp + kChViews + chh, (s1 - c.y * s2) * ld_shared_f32(rinv_a));
             }
 
             // ================= dgrad chain =================
@@ -260,17 +267,16 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 const uint32_t hi = (f & JB_HI_HALF) ? 1u : 0u;
                 const uint32_t chh = 128u * hi + cl;                       // channel within the layer
                 const float2 c = c_next;
-                const float wa = (f & JB_ADD_ALPHA) ? __ldg(&g_wa[chh]) : 0.0f;
                 const uint8_t* hrow = saved_row(g, jb.slot, chh);
-                const uint32_t row_addr = opaque_u32(act + (chh >> 3) * kKGroup3 + pq * kNGroup3 + (chh & 7u) * 128u);
+                const uint32_t row_addr = act + (chh >> 3) * kKGroup3 + pq * kNGroup3 + (chh & 7u) * 128u;
                 const uint32_t swz = (chh & 7u) << 4;
                 // saved activations: two chunks are requested before the accumulator is waited for, then each consumed
                 // slot is refilled with the chunk two ahead
                 H32 hh[2];
                 hh[0] = ldg_nc_32B(hrow + pair_off(0, swz));
                 hh[1] = ldg_nc_32B(hrow + pair_off(1, swz));
-                prefetch_slice(slice_ptr(g, j + 2));          // the job after next, into L2 (one line per thread)
-                if (j + 2 == kBwd3Jobs + 1) prefetch_slice(slice_ptr(g, j + 3));
+                prefetch_seq(g, j + 3);            // the job after next, into L2 (one line per thread)
+                if (j == kBwd3Jobs - 1) prefetch_seq(g, j + 4);
                 unsigned long long tj0 = 0;
                 if (tracing) tj0 = clock64();
                 if (hi) { mbar_wait(bar(kB3AccReady + 1), ph_acc1); ph_acc1 ^= 1; }
@@ -280,14 +286,15 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 c_next = __ldg(&g_sb[prm.prog.job[j + 1 < kBwd3Jobs ? j + 1 : 0].ch + cl]);        // in flight during this job
                 const uint32_t ta = tmem_lane + (hi ? 256u : 0u);
                 const bool relu = f & JB_RELU, write = !(f & JB_NO_WRITE);
-                const __half2 es2 = __float2half2_rn(c.x);
                 float s1 = 0.0f, s2 = 0.0f;
                 uint32_t va[16];
-                tmem_ld16(ta, va);
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    tmem_ld_wait();
-                    if (f & JB_ADD_ALPHA) {        // d h8 also receives the alpha head's gradient
+                if (f & JB_ADD_ALPHA) {        // d h8 also receives the alpha head's gradient: one job in 18, done as a
+                                               // read-modify-write pass over the accumulator so the chunk loop stays lean
+                    const float wa = __ldg(&g_wa[chh]);
+#pragma unroll 1
+                    for (int cc = 0; cc < 4; ++cc) {
+                        tmem_ld16(ta + 16 * cc, va);
+                        tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 16; i += 4) {
                             const float4 ga = ld_shared_v4f(ga_a + 4 * (cc * 16 + i));
@@ -296,7 +303,14 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                             va[i + 2] = __float_as_uint(fmaf(ga.z, wa, __uint_as_float(va[i + 2])));
                             va[i + 3] = __float_as_uint(fmaf(ga.w, wa, __uint_as_float(va[i + 3])));
                         }
+                        tmem_st16(ta + 16 * cc, va);
                     }
+                    tmem_st_wait();
+                }
+                tmem_ld16(ta, va);
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    tmem_ld_wait();
                     // fp16 copy of the gradients; the accumulator registers are then free for the next chunk's load,
                     // which is in flight while this chunk is processed
                     uint32_t dpk[8];
@@ -306,10 +320,10 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                     if (cc == 0 && (f & JB_WAIT_SF)) { mbar_wait(bar(kB3StageFree + (q >> 1)), ph_sf); ph_sf ^= 1; }
                     const H32 hp = hh[cc & 1];
                     if (cc < 2) hh[cc & 1] = ldg_nc_32B(hrow + pair_off(cc + 2, swz));       // refill with chunk cc + 2
-                    chunk16(dpk, hp.a, hp.b, es2, relu, write, row_addr, swz, cc, s1, s2);
+                    chunk16(dpk, hp.a, hp.b, relu, write, row_addr, swz, cc, s1, s2);
                 }
                 if (write || hi) publish(hi ? kB3ActHi : kB3ActLo);
-                red_global_add_f32(prm.grad_tmp + jb.ch + cl, (s1 - c.y * (s2 / c.x)) * rinv);     // after the hand-over
+                red_global_add_f32(prm.grad_tmp + jb.ch + cl, (s1 - c.y * s2) * ld_shared_f32(rinv_a));     // after the hand-over
                 if (tracing) t_job += clock64() - tj0;
             }
         }

@@ -49,7 +49,10 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
     auto bar = [&](int i) { return sbase + kS3Bars + 8u * i; };
 
     for (int i = threadIdx.x; i < 256; i += kThreads3) out_s[i] = 0.0f;
-    const uint32_t tmem_base = setup3(smem, sbase, warp);
+    // the CTA owns the SM (1 CTA/SM by shared-memory size) and allocates all 512 TMEM columns, so the allocation starts
+    // at column 0; treating the base as a constant frees a register in every epilogue thread
+    constexpr uint32_t tmem_base = 0;
+    if (setup3(smem, sbase, warp) != tmem_base) __trap();
     const int first = blockIdx.x, stride = gridDim.x;
     const int n_iters = first < prm.n_groups ? (prm.n_groups - first + stride - 1) / stride : 0;
 

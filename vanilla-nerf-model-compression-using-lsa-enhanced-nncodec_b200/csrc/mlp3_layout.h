@@ -138,6 +138,9 @@ struct Prog3Fwd {
 struct Prog3Bwd {
     Half3 half[kBwd3Jobs];
     Job3 job[kBwd3Jobs];
+    // byte offset, inside a group's saved activations, of the 64 KB slice each epilogue job of a group reads, in
+    // execution order: [0] the views-gradient prologue job, [1 + j] job j (used for L2 prefetching)
+    uint32_t slice_off[kBwd3Jobs + 1];
 };
 
 // Forward program.  Waits and arrivals pair up exactly (see mlp3.cu):
@@ -222,16 +225,23 @@ inline Prog3Bwd make_prog3_bwd() {
             e.ch = (int16_t)(st.ch + 128 * mh);
             e.slot = (int16_t)(8 - s);
             e.flags = (uint16_t)f;
+            p.slice_off[1 + j] = (uint32_t)(e.slot * (16 * 256 * 32) + mh * (128 * 32));
         }
     }
+    p.slice_off[0] = 9u * (16 * 256 * 32);
     return p;
 }
 
 // ---- packed network buffer: weight images after the small fields of net_layout.h -----------------
 constexpr size_t kOffFwd3Image = (kPackedBytes + 1023) / 1024 * 1024;
 constexpr size_t kOffBwd3Image = kOffFwd3Image + kFwd3ImageBytes;
+// The backward image holds W^T * (delta * lsa_scale) per output channel of W (the contraction index of the dgrad
+// GEMM), rebuilt by nerfq_set_scale_bias from the integer-level copy below, so that the backward epilogue hands the
+// masked gradient itself to the next GEMM instead of multiplying every element by the channel's scale.
 constexpr size_t kOffGradTmp3 = kOffBwd3Image + kBwd3ImageBytes;          // float[2440] backward scratch (kept zeroed)
-constexpr size_t kPacked3Bytes = kOffGradTmp3 + 4 * 2440;
+constexpr size_t kOffBwd3Levels = (kOffGradTmp3 + 4 * 2440 + 1023) / 1024 * 1024;     // backward image, integer levels
+constexpr size_t kOffBwd3StageCh = kOffBwd3Levels + kBwd3ImageBytes;      // int[2 * kBwd3Chunks]: channel of k = 0 per stage
+constexpr size_t kPacked3Bytes = kOffBwd3StageCh + 4 * 2 * kBwd3Chunks;
 
 // ---- saved activations (forward with `save`, read by the backward) ------------------------------------------
 // Per group of 256 points ten slots (h1..h8, feature, views hidden) of 128 KB, each laid out

@@ -45,7 +45,8 @@ __global__ void pack_images3_kernel(const PackParams p, const Step3Tables tabs) 
     int sidx = bwd ? blockIdx.x - n_fwd : blockIdx.x;
     const Step3* tab = bwd ? tabs.bwd : tabs.fwd;
     const int nsteps = bwd ? kBwd3Steps : kFwd3Steps;
-    uint8_t* dst = p.packed + (bwd ? kOffBwd3Image : kOffFwd3Image) + (size_t)sidx * kStage3Bytes;
+    uint8_t* dst = p.packed + (bwd ? kOffBwd3Levels : kOffFwd3Image) + (size_t)sidx * kStage3Bytes;
+    const int stage = sidx;
     int s = 0;
     for (; s < nsteps; ++s) {
         const int n = tab[s].halves * (tab[s].kh + tab[s].kp);
@@ -56,6 +57,8 @@ __global__ void pack_images3_kernel(const PackParams p, const Step3Tables tabs) 
     const int per_half = st.kh + st.kp;
     const int mh = sidx / per_half, j = sidx % per_half;
     const int in = kInDev[st.layer], out = kOutDev[st.layer];
+    if (bwd && threadIdx.x == 0)        // the stage's 32 contraction indices are output channels 32 j .. of this layer
+        reinterpret_cast<int*>(p.packed + kOffBwd3StageCh)[stage] = kChDev[st.layer] + 32 * j;
     for (int item = threadIdx.x; item < 128 * 4; item += blockDim.x) {
         const int r = item >> 2, chunk = item & 3;
         float v[8];
@@ -112,11 +115,37 @@ __global__ void pack_small_kernel(const PackParams p) {
 }
 
 // sb[ch] = {delta[ch] * scale[ch], bias[ch]};  scale == nullptr means 1 (no LSA).
+// Blocks kScaleBlocks.. rebuild the backward weight image: level * delta * scale of the contraction channel, one
+// 8 KB stage per block.
+constexpr int kScaleBlocks = 5;
 __global__ void set_scale_bias_kernel(uint8_t* packed, const float* __restrict__ scale, const float* __restrict__ bias) {
     const float* delta = reinterpret_cast<const float*>(packed + kOffDelta);
+    if ((int)blockIdx.x >= kScaleBlocks) {
+        const int stage = blockIdx.x - kScaleBlocks;
+        const int ch0 = reinterpret_cast<const int*>(packed + kOffBwd3StageCh)[stage];
+        const uint4* src = reinterpret_cast<const uint4*>(packed + kOffBwd3Levels + (size_t)stage * kStage3Bytes);
+        uint4* dst = reinterpret_cast<uint4*>(packed + kOffBwd3Image + (size_t)stage * kStage3Bytes);
+        for (int u = threadIdx.x; u < kStage3Bytes / 16; u += blockDim.x) {
+            const int row = u >> 2, chunk = (u & 3) ^ ((row >> 1) & 3);           // inverse of sw64_offset
+            const uint4 q = src[u];
+            const uint32_t in[4] = {q.x, q.y, q.z, q.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&in[e]));
+                int c0 = ch0 + chunk * 8 + 2 * e, c1 = c0 + 1;                    // padded rows hold zero levels
+                c0 = c0 < kNumChannels ? c0 : kNumChannels - 1;
+                c1 = c1 < kNumChannels ? c1 : kNumChannels - 1;
+                const float e0 = delta[c0] * (scale ? scale[c0] : 1.0f), e1 = delta[c1] * (scale ? scale[c1] : 1.0f);
+                o[e] = pack_half2(v.x * e0, v.y * e1);
+            }
+            dst[u] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        return;
+    }
     float2* sb = reinterpret_cast<float2*>(packed + kOffSB);
     float* sc = reinterpret_cast<float*>(packed + kOffScale);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kNumChannels; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kNumChannels; i += kScaleBlocks * blockDim.x) {
         const float s = scale ? scale[i] : 1.0f;
         sc[i] = s;
         sb[i] = make_float2(delta[i] * s, bias[i]);
@@ -152,6 +181,6 @@ extern "C" int nerfq_pack_net(void* packed, const void* const* weights12, const 
 extern "C" int nerfq_set_scale_bias(void* packed, const float* scale, const float* bias, cudaStream_t stream) {
     using namespace nerfq;
     if (!packed || !bias) return -1;
-    set_scale_bias_kernel<<<5, 512, 0, stream>>>(reinterpret_cast<uint8_t*>(packed), scale, bias);
+    set_scale_bias_kernel<<<kScaleBlocks + 2 * kBwd3Chunks, 512, 0, stream>>>(reinterpret_cast<uint8_t*>(packed), scale, bias);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
