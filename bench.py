@@ -33,7 +33,7 @@ FLOP_PER_POINT_FWD = 2 * 593408
 FLOP_PER_POINT_BWD = 2 * 557696
 METRIC = "rays/sec render_rays (64+128 samples/ray); LSA steps/sec"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 4096 rays x 192 samples (profiles/)
-NCU_DRAM_BYTES = {"mlp_bwd_fine": None, "mlp_fwd_fine": None}
+NCU_DRAM_BYTES = {"mlp_bwd_fine": 3922807000 + 14878720, "mlp_fwd_fine": 4742656 + 3799448000}      # profiles/r01_ncu_mlp_kernels_summary.txt
 
 
 def synth_batch(n, seed, device="cpu"):
@@ -314,7 +314,15 @@ def run_cuda(args):
                 line["cpu_baseline"] = {"value": None, "unit": "rays/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # The captured graphs hold NCCL work; tearing the process group down under them was seen to hang.  Drop the
+        # graphs, drain the device, meet the other ranks once more and leave without the interpreter's teardown.
+        step_main.graph = step_noq.graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

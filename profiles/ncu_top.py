@@ -1,5 +1,5 @@
 """Summarise an ncu report's source page: top SASS instructions by stall samples (with the dominant stall reasons)
-and per-64-instruction-window sample totals.  usage: python profiles/ncu_top.py report.ncu-rep [n_top]"""
+and per-64-instruction-window sample totals.  usage: python profiles/ncu_top.py report.ncu-rep [n_top [kernel_index]]"""
 import csv
 import subprocess
 import sys
@@ -8,7 +8,12 @@ rep = sys.argv[1]
 n_top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-hdr, data = rows[1], rows[2:]
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0            # a report may hold several kernels: pick one
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] or [0]
+lo = starts[which]
+hi = starts[which + 1] if which + 1 < len(starts) else len(rows)
+rows = rows[lo:hi]
+hdr, data = rows[1], [r for r in rows[2:] if len(r) >= len(rows[1])]
 ia, isrc, isamp, iex = hdr.index("Address"), hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 tot = sum(int(r[isamp] or 0) for r in data)
