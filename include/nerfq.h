@@ -61,7 +61,9 @@ int nerfq_num_channels(void);
 int nerfq_pack_net(void* packed, const void* const* weights12, const float* delta12, int src_is_int32,
                    nerfq_stream_t stream);
 
-/* Epilogue constants {delta*scale, bias} per output channel; scale == NULL means no LSA (scale 1). */
+/* Epilogue constants {delta*scale, bias} per output channel; scale == NULL means no LSA (scale 1).  Must follow every
+ * nerfq_pack_net and every change of the scales: it also rebuilds the backward weight image (level * delta * scale,
+ * transforms.py:104-111 folded into the dgrad operand) that nerfq_mlp_backward streams. */
 int nerfq_set_scale_bias(void* packed, const float* scale, const float* bias, nerfq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
