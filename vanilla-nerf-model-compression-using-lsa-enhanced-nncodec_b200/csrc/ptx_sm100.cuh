@@ -212,6 +212,11 @@ __host__ __device__ __forceinline__ uint32_t sw64_offset(uint32_t row, uint32_t 
 
 // explicit shared-space accesses with 32-bit addresses (a pointer derived from the manually aligned dynamic
 // shared-memory base is a generic pointer to the compiler, which would emit generic ST/ATOM instead of STS/ATOMS)
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
