@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 
 #include "mlp3_common.cuh"
+#include "mlp4_fwd.h"
 
 namespace nerfq {
 
@@ -253,8 +254,11 @@ static int g_trace3_flags = 0;
 // writes 8 cycle counters per CTA into this device buffer (see profiles/trace_v3.py).
 extern "C" void nerfq_mlp_set_trace(unsigned long long* buf, int flags) { g_trace3 = buf; g_trace3_flags = flags; }
 
-extern "C" int nerfq_mlp_forward(const void* packed, const float* rays, const float* z, long long n_rays, int samples_per_ray,
-                                  float* raw, void* save, int max_ctas, cudaStream_t stream) {
+bool nerfq::mlp3_forward_tracing() { return g_trace3 != nullptr; }
+
+// The single-CTA schedule; nerfq_mlp_forward (mlp4_fwd.cu) dispatches here for A/B measurements and tracing.
+int nerfq::mlp3_forward_launch(const void* packed, const float* rays, const float* z, long long n_rays, int samples_per_ray,
+                               float* raw, void* save, int max_ctas, cudaStream_t stream) {
     using namespace nerfq;
     if (n_rays == 0) return 0;
     if (!packed || !rays || !z || !raw || n_rays < 0 || samples_per_ray <= 0) return -1;
