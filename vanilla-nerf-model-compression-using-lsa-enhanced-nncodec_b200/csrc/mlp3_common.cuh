@@ -114,21 +114,30 @@ __device__ __forceinline__ void issuer3(uint32_t sbase, uint32_t tmem_base, cons
     const uint64_t b_act0 = umma_desc_mn3(sbase + kS3Act);
     const uint64_t b_enc0 = umma_smem_desc(sbase + kS3Enc, 1024, SWZ_128B);
     uint32_t seq = 0, ph_lo = 0, ph_hi = 0;
+    bool slot_probed = false;          // the previous chunk already saw this chunk's weights in the ring
     // one weight chunk: 4 MMAs; stage 1 of the B operand starts `stage` (16-byte units) after stage 0, the second
-    // K=16 half of a stage `kstep` after the first
+    // K=16 half of a stage `kstep` after the first.  The tensor pipe queues ~2 MMAs, so after the first two the issue
+    // of the third blocks until the first retires: that time is used to probe the NEXT chunk's "slot full" barrier,
+    // which takes the ~130-cycle barrier wait out of the gap between chunks whenever the loader is ahead.
     auto chunk = [&](uint32_t d_tmem, uint64_t b, uint32_t idesc, uint32_t kstep, uint32_t stage, uint32_t accumulate,
                      uint32_t commit_a, uint32_t commit_b) {
         const uint32_t slot = seq & (kSlots3 - 1), par = (seq >> 2) & 1;
         ++seq;
-        unsigned long long t0 = 0;
-        if (kTrace) t0 = clock64();
-        mbar_wait(bar0 + 8 * (kB3WFull + slot), par);
+        if (!slot_probed) {
+            unsigned long long t0 = 0;
+            if (kTrace) t0 = clock64();
+            mbar_wait(bar0 + 8 * (kB3WFull + slot), par);
+            if (kTrace) t_w += clock64() - t0;
+        }
         tc_fence_after_sync();
-        if (kTrace) t_w += clock64() - t0;
+        const uint64_t ad = a_desc0 + slot * (kChunk3Bytes >> 4);
         if (elect_one()) {
-            const uint64_t ad = a_desc0 + slot * (kChunk3Bytes >> 4);
             umma_ss(d_tmem, ad, b, idesc, accumulate);
             umma_ss(d_tmem, ad + 2, b + kstep, idesc, 1u);
+        }
+        __syncwarp();
+        slot_probed = __all_sync(0xffffffffu, mbar_test_wait(bar0 + 8 * (kB3WFull + (seq & (kSlots3 - 1))), (seq >> 2) & 1));
+        if (elect_one()) {
             umma_ss(d_tmem, ad + (kStage3Bytes >> 4), b + stage, idesc, 1u);
             umma_ss(d_tmem, ad + (kStage3Bytes >> 4) + 2, b + stage + kstep, idesc, 1u);
             umma_commit(bar0 + 8 * (kB3WEmpty + slot));
