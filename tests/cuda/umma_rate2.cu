@@ -65,12 +65,9 @@ __device__ __forceinline__ uint32_t cluster_rank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 
 template <int kMode>
-__device__ __forceinline__ void issue16(uint32_t tmem, uint64_t a0, uint64_t b0, uint32_t idesc) {
+__device__ __forceinline__ void issue16(uint32_t tmem, uint64_t a0, uint64_t b0, uint32_t idesc, uint32_t cbar = 0) {
     // 8 distinct K=16 steps of the K=128 operands, twice
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -82,6 +79,13 @@ __device__ __forceinline__ void issue16(uint32_t tmem, uint64_t a0, uint64_t b0,
             } else if (kMode == 1) {
                 // A: SW128 K-major as above; B: MN-major tile, 2 K-groups of 4 KB per step
                 umma_ss_c<1>(tmem, a0 + (((k >> 2) * 16384 + (k & 3) * 32) >> 4), b0 + ((k * 8192) >> 4), idesc);
+            } else if (kMode == 5) {
+                // as mode 1, plus a commit after every 4 MMAs (what the MLP kernels do per 16 KB weight chunk)
+                umma_ss_c<1>(tmem, a0 + (((k >> 2) * 16384 + (k & 3) * 32) >> 4), b0 + ((k * 8192) >> 4), idesc);
+                if ((k & 3) == 3) umma_commit(cbar + 8 * (k >> 2));
+            } else if (kMode == 4) {
+                // A: SWIZZLE_64B K-major stages of [128 rows x 32 k] (8 KB), two K=16 steps per stage; B: MN-major tile
+                umma_ss_c<1>(tmem, a0 + (((k >> 1) * 8192 + (k & 1) * 32) >> 4), b0 + ((k * 8192) >> 4), idesc);
             } else if (kMode == 2) {
                 umma_ts(tmem, (uint32_t)a0 + k * 8, b0 + (((k >> 2) * 32768 + (k & 3) * 32) >> 4), idesc);
             } else {
@@ -129,9 +133,10 @@ __global__ void __launch_bounds__(384, 1) rate2_kernel(const Args a) {
     if (warp == 0) {
         if (lane == 0 && rank == 0) {
             const uint32_t idesc = (1u << 4) | ((uint32_t(a.n) >> 3) << 17) | (((a.mode == 3 ? 256u : 128u) >> 4) << 24) |
-                                   (a.mode == 1 ? (1u << 16) : 0u);
-            const uint64_t a0 = (a.mode == 2) ? (uint64_t)(tmem + 256) : umma_smem_desc(sbase + kA, 1024, SWZ_128B);
-            const uint64_t b0 = (a.mode == 1) ? desc_mn(sbase + kB, 1024, 4096) : umma_smem_desc(sbase + kB, 1024, SWZ_128B);
+                                   ((a.mode == 1 || a.mode == 4 || a.mode == 5) ? (1u << 16) : 0u);
+            const uint64_t a0 = (a.mode == 2) ? (uint64_t)(tmem + 256)
+                                : (a.mode == 4 ? umma_smem_desc(sbase + kA, 512, SWZ_64B) : umma_smem_desc(sbase + kA, 1024, SWZ_128B));
+            const uint64_t b0 = (a.mode == 1 || a.mode == 4 || a.mode == 5) ? desc_mn(sbase + kB, 1024, 4096) : umma_smem_desc(sbase + kB, 1024, SWZ_128B);
             const unsigned long long t0 = clock64();
             if (a.mode < 0) {
                 while (clock64() - t0 < 400000ull) {}
@@ -142,6 +147,8 @@ __global__ void __launch_bounds__(384, 1) rate2_kernel(const Args a) {
                     } else {
                         if (a.mode == 0) issue16<0>(tmem, a0, b0, idesc);
                         else if (a.mode == 1) issue16<1>(tmem, a0, b0, idesc);
+                        else if (a.mode == 4) issue16<4>(tmem, a0, b0, idesc);
+                        else if (a.mode == 5) issue16<5>(tmem, a0, b0, idesc, bar(2));
                         else issue16<2>(tmem, a0, b0, idesc);
                     }
                 }
@@ -225,17 +232,15 @@ int main() {
     cudaMalloc(&d_dst, (size_t)sms * 3 << 20);
     cudaFuncSetAttribute(rate2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     cudaFuncSetAttribute(rate2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    const char* names[] = {"none (spin)", "SS A K / B K   ", "SS A K / B MN  ", "TS A tmem / B K", "2CTA SS M=256  "};
+    const char* names[] = {"none (spin)", "SS A K / B K   ", "SS A K / B MN  ", "TS A tmem / B K", "2CTA SS M=256  ", "SS A K SW64/B MN", "B MN + commit/4 "};
     struct Exp { int mode, n, sts, bulk, lanes, slots, chunk; };
     std::vector<Exp> exps;
-    exps.push_back({0, 256, 0, 0, 1, 1, 16384});
-    for (int mode : {-1, 0, 1}) {
-        exps.push_back({mode, 256, 0, -1, 1, 4, 16384});
-        exps.push_back({mode, 256, 0, -3, 1, 4, 16384});
-        exps.push_back({mode, 256, 0, -3, 1, 4, 1024});
-        exps.push_back({mode, 256, 0, -3, 1, 4, 4096});
-        exps.push_back({mode, 256, 8, -3, 1, 4, 4096});
-    }
+    // A-operand swizzle: 128-byte rows (64 k per row) against the 64-byte rows (32 k) of the MLP weight stages
+    for (int mode : {1, 5})
+        for (int n : {256, 128}) {
+            exps.push_back({mode, n, 0, 0, 1, 1, 16384});
+            exps.push_back({mode, n, 8, 0, 1, 1, 16384});
+        }
     for (int grid : {sms}) {
         for (const Exp& e : exps) {
             Args a{e.mode, e.n, 512, e.sts, e.bulk, e.lanes, e.slots, e.chunk, d_src, d_dst, d_out};
