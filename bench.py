@@ -286,8 +286,9 @@ def run_cuda(args):
                 "clocks": clocks}
         # launches of OUR kernels per step: pack_rays 1, per network pass: set_scale_bias 1 + mlp_fwd 1 + composite_fwd 1,
         # coarse_depths 1, sample_fine 1, mse_grad 0 (torch), bwd: 2 x (composite_bwd 1 + mlp_bwd 1 + finalize 1);
-        # requantise: absmax + quantize (batched over the 48 tensors) + 2 nets x 2 pack kernels
-        per_step = 1 + 2 * 3 + 1 + 1 + 2 * 3 + (2 + 4 if requant_each_step else 0)
+        # requantise: absmax + quantize (batched over the 48 tensors) + 2 nets x (2 pack kernels + set_scale_bias);
+        # matches the ncu launch list (profiles/r01_launches_lsa_step_summary.txt: 23 of the 54 launches are nerfq kernels)
+        per_step = 1 + 2 * 3 + 1 + 1 + 2 * 3 + (2 + 6 if requant_each_step else 0)
         line["gpu_launches"] = per_step * args.steps
         if world == 1:
             rows = {k: {"ms": v[0], "tflops": v[1] / (v[0] * 1e-3) / 1e12} for k, v in kern.items()}
