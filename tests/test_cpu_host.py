@@ -150,3 +150,34 @@ def test_lsa_parameter_selection_matches_tune_model():
     assert len(trainable) == 24 and all(n.endswith("weight_scaling") for n in trainable)
     with pytest.raises(RuntimeError):
         lsa.LSAStep(w, 16)
+
+
+def test_deepcabac_front_end_contract():
+    """nerfq_b200.deepcabac keeps the names baseline.py:24-57,89-98 binds; what is not on the GPU path refuses loudly
+    (no silent CPU fallback); argument errors are raised before any device work; empty tensors are accepted."""
+    import numpy as np
+    import pytest
+    from nerfq_b200 import deepcabac
+    enc, dec = deepcabac.Encoder(), deepcabac.Decoder()
+    for name in ("initCtxModels", "quantLayer", "iae_v", "encodeLayer", "finish"):
+        assert callable(getattr(enc, name))
+    for name in ("setStream", "initCtxModels", "iae_v", "decodeLayer", "decodeLayerAndCreateEPs", "setEntryPoints", "dequantLayer", "finish"):
+        assert callable(getattr(dec, name))
+    enc.initCtxModels(10, 0)
+    w = np.ones((4, 3), dtype=np.float32)
+    out = np.zeros((4, 3), dtype=np.int32)
+    with pytest.raises(NotImplementedError):
+        enc.quantLayer(w, out, 1, 2, -20, 0.0, 10, 0)              # dependent quantisation stays on the host coder
+    with pytest.raises(NotImplementedError):
+        enc.encodeLayer(out, 0, 0)
+    with pytest.raises(NotImplementedError):
+        dec.decodeLayer(out, 0, 0)
+    with pytest.raises(TypeError):
+        enc.quantLayer(w.astype(np.float64), out, 0, 2, -20, 0.0, 10, 0)
+    with pytest.raises(ValueError):
+        enc.quantLayer(np.ones((3, 4), dtype=np.float32).T, out, 0, 2, -20, 0.0, 10, 0)      # transposed view, baseline.py:34-36
+    with pytest.raises(ValueError):
+        dec.dequantLayer(np.zeros(5, dtype=np.float32), np.zeros(4, dtype=np.int32), 2, -20, 0)
+    e_w, e_l = np.zeros((0, 7), dtype=np.float32), np.zeros((0, 7), dtype=np.int32)
+    assert enc.quantLayer(e_w, e_l, 0, 2, -20, 0.0, 10, 0) == -20
+    dec.dequantLayer(e_w, e_l, 2, -20, 0)

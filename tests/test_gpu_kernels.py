@@ -204,3 +204,26 @@ def test_quantizer_batch_bit_exact(dev):
             assert (lv[i].cpu().numpy() == lv_ref).all(), (i, qp)
             assert (ts[i].cpu().numpy() == qo.dequant(lv_ref, used_ref, 2)).all(), (i, qp)
     assert int(used[-1]) > -75                                  # the last tensor forces the qp clip
+
+
+def test_deepcabac_front_end_matches_oracle(dev):
+    """The calls nnc_core/approximator/baseline.py makes (approx :39-62, rec :89-98), through nerfq_b200.deepcabac with
+    numpy arrays allocated the way the reference allocates them, against the C oracle: levels, clipped qp, values."""
+    from nerfq_b200 import deepcabac
+    from oracle import quant_oracle as qo
+    rng = np.random.default_rng(11)
+    params = {"w": (rng.standard_normal((256, 319)) * 0.1).astype(np.float32), "b": (rng.standard_normal((256,)) * 0.01).astype(np.float32),
+              "ls": (1.0 + 1e-3 * rng.standard_normal((256, 1))).astype(np.float32), "clip": np.array([[3e4, -1.0, 0.3]], dtype=np.float32)}
+    qps = {"w": -20, "b": -75, "ls": -75, "clip": -75}
+    encoder = deepcabac.Encoder()
+    for name, values in params.items():
+        quantized = np.zeros(values.shape, dtype=np.int32)
+        encoder.initCtxModels(10, 0)
+        qp = encoder.quantLayer(values, quantized, 0, 2, qps[name], 0.0, 10, 0)
+        lv_ref, used_ref = qo.quant_urq(values, qps[name], 2)
+        assert qp == used_ref and (quantized == lv_ref).all(), name
+        assert (qp != qps[name]) == (name == "clip")
+        rec = np.zeros(values.shape, dtype=np.float32)
+        deepcabac.Decoder().dequantLayer(rec, quantized, 2, qp, 0)
+        assert (rec == qo.dequant(lv_ref, used_ref, 2)).all(), name
+        assert np.abs(rec - values).max() <= 0.5 * qo.stepsize(qp, 2) * (1 + 1e-6)
