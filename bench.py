@@ -111,27 +111,43 @@ def oracle_model(seed=0):
     return p
 
 
-def cpu_lsa_steps(p, n_rays, steps, warmup, seed=2):
-    """LSA steps of the oracle on `n_rays` rays with Adam on the scales; returns (sec per step, threads)."""
+def cpu_lsa_steps(p, n_rays, steps, warmup, seed=2, device=None):
+    """LSA steps of the oracle on `n_rays` rays with Adam on the scales; returns (sec per step, threads).
+    device=None: host cores (the cpu_baseline).  device=cuda: the same stock-torch code on the GPU, i.e. what the
+    reference's eager path achieves on this box (secondary comparison point) -- a baseline, never the product."""
     from oracle import render_oracle as ro
+    import contextlib
     o, d, target = synth_batch(n_rays, seed)
     batch, _ = ro.pack_rays(4, 4, None, rays=(o, d), ndc=False, near=2.0, far=6.0)
+    on_gpu = device is not None
+    if on_gpu:
+        batch, target = batch.to(device), target.to(device)
+        p = {k: v.to(device) for k, v in p.items()}
     scales = {k: v.clone().requires_grad_(True) for k, v in p.items() if k.endswith("weight_scaling")}
     frozen = {k: v for k, v in p.items() if not k.endswith("weight_scaling")}
     opt = torch.optim.Adam(list(scales.values()), lr=1e-4)
     g = torch.Generator().manual_seed(5)
     times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        t_rand = torch.rand(n_rays, N_SAMPLES, generator=g)
-        u = torch.rand(n_rays, N_IMPORTANCE, generator=g)
-        out = ro.render_rays({**frozen, **scales}, batch, N_SAMPLES, N_IMPORTANCE, white_bkgd=True, t_rand=t_rand, u=u)
-        loss = ro.lsa_loss(out, target)
-        loss.backward()
-        opt.step()
-        opt.zero_grad()
-        if it >= warmup:
-            times.append(time.perf_counter() - t0)
+    with (torch.device(device) if on_gpu else contextlib.nullcontext()):      # factory calls inside the oracle follow the device
+        for it in range(warmup + steps):
+            if on_gpu:
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if on_gpu:
+                t_rand = torch.rand(n_rays, N_SAMPLES, device=device)
+                u = torch.rand(n_rays, N_IMPORTANCE, device=device)
+            else:
+                t_rand = torch.rand(n_rays, N_SAMPLES, generator=g)
+                u = torch.rand(n_rays, N_IMPORTANCE, generator=g)
+            out = ro.render_rays({**frozen, **scales}, batch, N_SAMPLES, N_IMPORTANCE, white_bkgd=True, t_rand=t_rand, u=u)
+            loss = ro.lsa_loss(out, target)
+            loss.backward()
+            opt.step()
+            opt.zero_grad()
+            if on_gpu:
+                torch.cuda.synchronize()
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
     return float(np.mean(times)), torch.get_num_threads()
 
 
@@ -313,6 +329,15 @@ def run_cuda(args):
                                         "sample": f"{sample}-ray LSA steps (fwd+bwd+Adam) of the oracle, torch CPU fp32, mean of 3 after 1 warm-up"}
             except Exception as ex:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": "rays/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+            # secondary comparison: the same stock-torch code on this GPU, full 4096-ray steps
+            try:
+                step_main.graph = step_noq.graph = None
+                torch.cuda.empty_cache()
+                sec, _ = cpu_lsa_steps(oracle_model(), RAYS_PER_GPU, 3, 2, device=dev)
+                line["torch_eager_gpu"] = {"value": RAYS_PER_GPU / sec, "unit": "rays/s",
+                                           "sample": "4096-ray LSA steps of the oracle port (stock torch fp32 eager + autograd + Adam) on this GPU, mean of 3 after 2 warm-ups"}
+            except Exception as ex:  # noqa: BLE001
+                line["torch_eager_gpu"] = {"value": None, "unit": "rays/s", "sample": f"failed: {str(ex)[:200]}"}
         print(json.dumps(line))
     if world > 1:
         # The captured graphs hold NCCL work; tearing the process group down under them was seen to hang.  Drop the
