@@ -102,7 +102,9 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
             c = make_float2(0.f, 0.f);
             wa = 0.0f;
             if (!(jn.flags & JB_FINAL)) c = __ldg(&g_sb[jn.ch + 32 * q + lane]);
-            if (jn.flags & JB_ALPHA) wa = __ldg(&g_wa[((jn.flags & JB_HI_HALF) ? 128 : 0) + 32 * q + lane]);
+            // alpha head weight of this channel as fixed-point logit units: level * (delta*scale of the head) * 2^20
+            if (jn.flags & JB_ALPHA)
+                wa = __ldg(&g_wa[((jn.flags & JB_HI_HALF) ? 128 : 0) + 32 * q + lane]) * __ldg(&g_sb[kChAlpha]).x * 1048576.0f;
         };
 
         float2 c_next = make_float2(0.f, 0.f);
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                                 }
                             }
                             const int pl = pq * 64 + cc * 32 + lane;
-                            const float sg = fmaf(ld_shared_f32(out_sa + 4 * pl), ca.x, ca.y);
+                            const float sg = fmaf((float)ld_shared_s32(out_sa + 4 * pl), 1.0f / 1048576.0f, ca.y);      // exact: |sum| < 2^24 logit-2^-20 units
                             st_shared_f32(out_sa + 4 * pl, 0.0f);
                             const long long gi = g0 + cc * 32 + lane;
                             if (gi < prm.n_points) prm.raw[4 * gi + 3] = sg;
@@ -203,11 +205,25 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                         st_shared_v4(row_addr + ((uint32_t)((cc * 2 + k) << 4) ^ swz), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
                     // the same 16 values go to the saved-activation slot: the warp's 32 channels are adjacent, 1 KB per store
                     if (kSave) st_global_v8(save_ch + save3_offset(pq * 4 + cc, 0), pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
-                    if (f & JB_ALPHA) {        // L7 is a ReLU layer: the head sees max(y, 0)
+                    if (f & JB_ALPHA) {
+                        // Alpha head over this warp's 32 channels (L7 is a ReLU layer: the head sees max(y, 0)), in fixed
+                        // point: each term  max(y,0) * level * (delta*scale) of the sigma logit is rounded to 2^-20, the
+                        // warp sum is one REDUX per point, and the eight partial sums of a point (4 warps x 2 halves) meet
+                        // in native integer shared-memory atomics.  Integer addition is associative, so sigma -- and with it
+                        // every pixel -- is bit-reproducible; a float butterfly + float atomics (a compare-and-swap loop
+                        // on sm_100) cost twice a normal job.  Range +-2048 logit units, rounding error < 4e-6 rms.
+                        int sum[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.0f) * wa;
-                        const float s = column_reduce16_3(y, lane);
-                        if (!(lane & 1)) red_shared_add_f32(out_sa + 4 * (pq * 64 + cc * 16 + (lane >> 1)), s);
+                        for (int i = 0; i < 16; ++i) sum[i] = __reduce_add_sync(0xffffffffu, __float2int_rn(fmaxf(y[i], 0.0f) * wa));
+                        // lane l (< 16) keeps the sum of point l: select tree on the lane bits
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) sum[i] = (lane & 8) ? sum[i + 8] : sum[i];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) sum[i] = (lane & 4) ? sum[i + 4] : sum[i];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) sum[i] = (lane & 2) ? sum[i + 2] : sum[i];
+                        const int mine = (lane & 1) ? sum[1] : sum[0];
+                        if (lane < 16) red_shared_add_s32(out_sa + 4 * (pq * 64 + cc * 16 + lane), mine);
                     }
                 };
                 {

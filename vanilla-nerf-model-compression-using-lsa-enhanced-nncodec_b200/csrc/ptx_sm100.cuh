@@ -295,6 +295,14 @@ __host__ __device__ __forceinline__ uint32_t sw64_offset(uint32_t row, uint32_t 
 
 // explicit shared-space accesses with 32-bit addresses (a pointer derived from the manually aligned dynamic
 // shared-memory base is a generic pointer to the compiler, which would emit generic ST/ATOM instead of STS/ATOMS)
+__device__ __forceinline__ void red_shared_add_s32(uint32_t addr, int v) {          // native (ATOMS.ADD), unlike the float form
+    asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_shared_s32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
