@@ -210,8 +210,8 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                         // point: each term  max(y,0) * level * (delta*scale) of the sigma logit is rounded to 2^-20, the
                         // warp sum is one REDUX per point, and the eight partial sums of a point (4 warps x 2 halves) meet
                         // in native integer shared-memory atomics.  Integer addition is associative, so sigma -- and with it
-                        // every pixel -- is bit-reproducible; a float butterfly + float atomics (a compare-and-swap loop
-                        // on sm_100) cost twice a normal job.  Range +-2048 logit units, rounding error < 4e-6 rms.
+                        // every pixel -- is bit-reproducible (a float butterfly + float atomics, a compare-and-swap loop
+                        // on sm_100, cost the same and were not).  Range +-2048 logit units, rounding error < 4e-6 rms.
                         int sum[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) sum[i] = __reduce_add_sync(0xffffffffu, __float2int_rn(fmaxf(y[i], 0.0f) * wa));
