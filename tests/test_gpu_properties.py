@@ -93,3 +93,26 @@ def test_quantiser_round_trip_whole_wrapper(dev, qp):
         assert torch.equal(lv, lv2)
         n += p.numel()
     assert n == 2 * 593408
+
+
+def test_cfg4_ndc_view_shard_invariance(dev, wrapper):
+    """378 x 504 forward-facing view in NDC (cfg4: near 0, far 1, rays warped by ndc_rays inside the ray kernel): the
+    second half of the image rendered as its own shard (first_pixel offset in the camera kernel) equals the same pixels
+    of the full render, bit for bit; disparity and accumulation stay finite and in range."""
+    from nerfq_b200 import ops, render as R
+    _, kw = R.create_nerf(wrapper, white_bkgd=False, dataset_type="llff")
+    H, W, focal = 378, 504, 407.5
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]], dtype=np.float32)
+    c2w = np.array([[1, 0, 0, 0.1], [0, 1, 0, -0.05], [0, 0, 1, 0.2]], dtype=np.float32)
+    kw = dict(kw)
+    for k in ("ndc", "near", "far"):
+        kw.pop(k, None)
+    with torch.no_grad():
+        rgb, disp, acc, _ = R.render(H, W, K, chunk=32768, c2w=torch.from_numpy(c2w), ndc=True, near=0.0, far=1.0, **kw)
+        first = (H // 2) * W
+        rays = ops.camera_rays(H, W, K, c2w, True, 0.0, 1.0, dev, first_pixel=first)
+        part = R.batchify_rays(rays, 32768, **{k: v for k, v in kw.items() if k not in ("use_viewdirs", "network_query_fn")})
+    assert rgb.shape == (H, W, 3) and torch.isfinite(rgb).all() and torch.isfinite(acc).all()
+    assert float(acc.min()) >= 0.0 and float(acc.max()) <= 1.0 + 1e-5
+    assert torch.equal(part["rgb_map"], rgb.reshape(-1, 3)[first:])
+    assert torch.equal(part["acc_map"], acc.reshape(-1)[first:])
