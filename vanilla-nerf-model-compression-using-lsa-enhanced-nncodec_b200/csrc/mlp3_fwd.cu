@@ -15,9 +15,12 @@
 // conversion, storing 8 points per 16-byte shared-memory store into the next layer's operand tile.  The epilogue of
 // channels 0..127 overlaps the MMAs of channels 128..255 and vice versa.  The alpha head is reduced on CUDA cores
 // in the L7 epilogue; the rgb head is one more (3-of-128-row) MMA.  With `save` set the fp16 activations are also
-// written to HBM for the backward pass, straight from the registers that feed the shared-memory store, in a
-// chunk-major layout that makes every warp store 1 KB contiguous (mlp3_layout.h).  (Letting the bulk-copy engine read
-// the tile back out of shared memory competes with the MMA operand reads: 11 B/clk/SM, profiles/r01_umma_rate2_bulk_store_vs_mma.log.)
+// written to HBM for the backward pass in a chunk-major layout that makes every warp store 1 KB contiguous
+// (mlp3_layout.h): half of a job's stores go straight from the registers that feed the shared-memory store, the other
+// half is read back from the tile after the hand-over, which spreads the stores over the time the warps would wait
+// for the next accumulator (the SM's store path is the limit while a job runs; kSaveInJob).  (Letting the bulk-copy
+// engine read the tile back out of shared memory competes with the MMA operand reads: 11 B/clk/SM,
+// profiles/r01_umma_rate2_bulk_store_vs_mma.log.)
 #include <cuda_runtime.h>
 
 #include "mlp3_common.cuh"
@@ -38,6 +41,8 @@ struct Fwd3Params {
     int dbg_flags;               // tracing build only: 1 skip TMEM loads, 2 skip operand stores, 4 skip conversion math
     Prog3Fwd prog;
 };
+
+constexpr int kSaveInJob = 2;      // chunks (of 4) whose saved activations are stored from registers inside the job; measured 1: 1.04, 2: 0.97, 3: 0.99, 4: 1.04 ms
 
 template <bool kSave, bool kTrace>
 __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid_constant__ Fwd3Params prm) {
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                     for (int k = 0; k < 2; ++k)
                         st_shared_v4(row_addr + ((uint32_t)((cc * 2 + k) << 4) ^ swz), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
                     // the same 16 values go to the saved-activation slot: the warp's 32 channels are adjacent, 1 KB per store
-                    if (kSave) st_global_v8(save_ch + save3_offset(pq * 4 + cc, 0), pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+                    if (kSave && cc < kSaveInJob) st_global_v8(save_ch + save3_offset(pq * 4 + cc, 0), pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
                     if (f & JB_ALPHA) {
                         // Alpha head over this warp's 32 channels (L7 is a ReLU layer: the head sees max(y, 0)), in fixed
                         // point: each term  max(y,0) * level * (delta*scale) of the sigma logit is rounded to 2^-20, the
@@ -249,6 +254,17 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                     }
                 }
                 publish(hi ? kB3ActHi : kB3ActLo);
+                if (kSave && kSaveInJob < 4) {
+                    // The SM's store path to L2 (~30 B/clk) is the limit while a job runs, and idle while the warps wait for
+                    // the next accumulator: the last chunks' saved activations are read back from the operand tile (only this
+                    // thread rewrites these rows, at the next layer) and stored after the hand-over.
+#pragma unroll
+                    for (int cc = kSaveInJob; cc < 4; ++cc) {
+                        const uint4 v0 = ld_shared_v4(row_addr + ((uint32_t)((cc * 2) << 4) ^ swz));
+                        const uint4 v1 = ld_shared_v4(row_addr + ((uint32_t)((cc * 2 + 1) << 4) ^ swz));
+                        st_global_v8(save_ch + save3_offset(pq * 4 + cc, 0), v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w);
+                    }
+                }
                 if (tracing) { const unsigned long long dt = clock64() - t0; t_job += dt; if (j == j_sel) t_sel += dt; }
             }
         }
