@@ -33,7 +33,7 @@ FLOP_PER_POINT_FWD = 2 * 593408
 FLOP_PER_POINT_BWD = 2 * 557696
 METRIC = "rays/sec render_rays (64+128 samples/ray); LSA steps/sec"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 4096 rays x 192 samples (profiles/)
-NCU_DRAM_BYTES = {"mlp_bwd_fine": 3922807000 + 14878720, "mlp_fwd_fine": 4742656 + 3799448000}      # profiles/r01_ncu_mlp_kernels_summary.txt
+NCU_DRAM_BYTES = {"mlp_bwd_fine": 3917792000 + 13829888, "mlp_fwd_fine": 4663552 + 3803394000}      # profiles/r01_ncu_mlp_kernels_summary.txt
 
 
 def synth_batch(n, seed, device="cpu"):
