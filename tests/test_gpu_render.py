@@ -121,3 +121,31 @@ def test_run_network_and_edge_cases(dev):
         assert maxerr(out["rgb_map"], ref["rgb_map"]) < GATE and maxerr(out["acc_map"], ref["acc_map"]) < GATE
     out = R.render_rays(torch.zeros(0, 11, device=dev), **test_kw)      # empty batch
     assert out["rgb_map"].shape == (0, 3)
+
+
+def test_apply_lsa_decoder_side_matches_lsa_model(dev):
+    """codec.apply_lsa (approximator/__init__.py:276-318: w *= ls, scales dropped) yields a plain wrapper whose render
+    equals the LSA model's, where the fused MLP applies delta*ls in its epilogue on integer-level operands: the two differ
+    only by the fp16 rounding of the folded weights."""
+    from nerfq_b200 import codec, model as nmodel, render as R
+    torch.manual_seed(4)
+    w = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params().to(dev)
+    with torch.no_grad():
+        for n, p in w.named_parameters():
+            if n.endswith("weight_scaling"):
+                p.copy_(1.0 + 0.05 * torch.randn_like(p))            # scales far enough from 1 to matter
+    codec.quantize_model(w, -20)
+    plain = codec.apply_lsa(w)
+    assert not any(k.endswith("weight_scaling") for k in plain.state_dict())
+    assert len(plain.state_dict()) == 48
+    sd, ps = w.state_dict(), plain.state_dict()
+    k = "model_fine.pts_linears.3"
+    assert torch.equal(ps[k + ".weight"], sd[k + ".weight"] * sd[k + ".weight_scaling"])
+    r = synth_rays(300, 9).to(dev)
+    rays = (r[:, :3].contiguous(), r[:, 3:6].contiguous())
+    _, kw_lsa = R.create_nerf(w, white_bkgd=True)
+    _, kw_plain = R.create_nerf(plain, white_bkgd=True)
+    with torch.no_grad():
+        a = R.render(4, 4, None, rays=rays, near=2.0, far=6.0, **kw_lsa)
+        b = R.render(4, 4, None, rays=rays, near=2.0, far=6.0, **kw_plain)
+    assert maxerr(a[0], b[0]) < GATE and maxerr(a[2], b[2]) < GATE

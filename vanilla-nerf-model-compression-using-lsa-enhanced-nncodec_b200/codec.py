@@ -64,3 +64,27 @@ def quantize_scales(wrapper, qp_density: int = 2, nonweight_qp: int = -75):
             if s is not None:
                 lv, _ = ops.quantize_urq(s.detach().float(), nonweight_qp, qp_density)
                 s.copy_(ops.dequantize(lv, nonweight_qp, qp_density))
+
+
+@torch.no_grad()
+def apply_lsa(wrapper):
+    """Decoder side of LSA (nnc_core/approximator/__init__.py:276-318): fold every `weight_scaling` into its weight,
+    `w *= ls.reshape(-1, 1, ...)`, and drop the scales.  Returns a plain NeRFWrapper (nn.Linear layers, no
+    `weight_scaling` entries in its state_dict) holding float32 weights `level * delta * ls` -- what
+    `decompress_model` hands to the test-view renderer.  The LSA model itself can be rendered without this detour:
+    the fused MLP applies `delta * ls` per output channel in its epilogue with the integer levels as operands."""
+    from .model import NeRFWrapper
+    src = wrapper.state_dict()
+    out = NeRFWrapper().to(next(wrapper.parameters()).device)
+    dst = out.state_dict()
+    for name, value in src.items():
+        if name.endswith("weight_scaling"):
+            continue
+        if name.endswith(".weight"):
+            ls = src.get(name[:-len("weight")] + "weight_scaling")
+            value = value * ls.reshape([-1] + [1] * (value.dim() - 1)) if ls is not None else value
+        dst[name].copy_(value)
+    for net in (out.model, out.model_fine):
+        net.quant_levels = None
+        net._packed = None
+    return out
