@@ -81,12 +81,11 @@ def test_lsa_step_oracle_larger(dev):
 
 
 def test_lsa_step_graph_replay_matches_eager(dev):
-    """nerfq_b200.lsa.LSAStep: three iterations replayed from the captured CUDA graph (perturb=0, requantise every
-    step) follow three eager iterations from the same start: same losses, same scale gradients (up to the summation
-    order of the float atomics), bit-identical integer levels.  The scales themselves are compared by their median
-    deviation only: Adam divides by |g| + 1e-8, so an element whose gradient is of the size of the atomics'
-    summation-order noise (1e-11 .. 1e-8 absolute here) moves by up to lr per step in either direction -- in the
-    eager path as much as in the replayed one."""
+    """nerfq_b200.lsa.LSAStep: three iterations (perturb=0, requantise every step) run eagerly, eagerly again, and replayed
+    from the captured CUDA graph end at bit-identical losses, gradients, scales and integer levels.  The whole iteration
+    is deterministic: partial sums that meet in arbitrary order (alpha head across warps, scale gradients across CTAs)
+    are accumulated in fixed point with integer atomics, and the graph records the update only (Adam's state is created
+    before the capture -- recorded inside it, every replay would restart the optimizer)."""
     import copy
     from nerfq_b200 import lsa, model as nmodel
     torch.manual_seed(3)
@@ -95,13 +94,13 @@ def test_lsa_step_graph_replay_matches_eager(dev):
     rays = torch.stack([r[:, :3], r[:, 3:6]], 0).contiguous().pin_memory()
     target = torch.rand(512, 3, generator=torch.Generator().manual_seed(6)).pin_memory()
     results = []
-    for graph in (False, True):
+    for mode in ("eager", "eager", "graph"):
         w = copy.deepcopy(base)
         master = {k: v.detach().clone() for k, v in w.state_dict().items()}
         rq = lsa.make_requantizer(w, master, -20)
         rq()
         step = lsa.LSAStep(w, 512, lr=1e-3, requantize=rq, perturb=0.0, white_bkgd=True)
-        if graph:
+        if mode == "graph":
             step.capture(warmup=0)
             assert step.graph is not None
         losses, first_grads = [], None
@@ -110,12 +109,13 @@ def test_lsa_step_graph_replay_matches_eager(dev):
             if i == 0:
                 first_grads = [p.grad.detach().clone() for p in step.params]
         results.append((losses, first_grads, [p.detach().clone() for p in step.params], [l.clone() for l in w.model_fine.quant_levels]))
-    (l0, g0, p0, q0), (l1, g1, p1, q1) = results
-    assert np.allclose(l0, l1, rtol=1e-5, atol=1e-7), (l0, l1)
+    l0, g0, p0, q0 = results[0]
     assert l0[2] != l0[0]                                  # the scales moved
-    for a, b in zip(g0, g1):
-        assert float((a - b).abs().max()) <= 2e-3 * float(a.abs().max()) + 1e-12     # measured 2e-4: float atomics, heavy cancellation
-    dev_all = torch.cat([(a - b).abs().reshape(-1) for a, b in zip(p0, p1)])
-    assert float(dev_all.median()) < 1e-5, float(dev_all.median())       # measured 2.6e-6 (lr = 1e-3, three steps)
-    for a, b in zip(q0, q1):
-        assert torch.equal(a, b)
+    for l1, g1, p1, q1 in results[1:]:
+        assert l0 == l1, (l0, l1)
+        for a, b in zip(g0, g1):
+            assert torch.equal(a, b)
+        for a, b in zip(p0, p1):
+            assert torch.equal(a, b)
+        for a, b in zip(q0, q1):
+            assert torch.equal(a, b)

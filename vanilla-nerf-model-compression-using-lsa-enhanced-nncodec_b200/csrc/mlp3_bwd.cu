@@ -28,7 +28,7 @@ struct Bwd3Params {
     const float* d_raw;      // [n_points, 4]
     const float* raw;        // [n_points, 4]   forward output (for the rgb / alpha head terms)
     const uint8_t* save;     // saved operand images from the forward pass (kSave3GroupBytes per group)
-    float* grad_tmp;         // [2436] scratch inside the packed buffer: sum_n dY (y - b) = s * ds, zero on entry
+    long long* grad_tmp;     // [2436] scratch inside the packed buffer: sum_n dY (y - b) = s * ds in fixed point, zero on entry
     long long n_points;
     int n_groups;
     unsigned long long* dbg;     // tracing build only: 8 cycle counters per CTA
@@ -36,17 +36,18 @@ struct Bwd3Params {
 };
 
 constexpr uint32_t kS3BwdGa = kS3BwdPg + 4096;          // float ga[256]: alpha-head gradient per point
-constexpr uint32_t kS3BwdMax = kS3BwdGa + 1024;         // uint gmax[2], float rinv[2]
-static_assert(kS3BwdMax + 16 <= kS3Misc, "backward scratch must fit the encoding-tile region");
+constexpr uint32_t kS3BwdMax = kS3BwdGa + 1024;         // uint gmax[2], float rinv, int group
+static_assert(kS3BwdMax + 32 <= kS3Misc, "backward scratch must fit the encoding-tile region");
 
 // one 128-byte line into L2
 __device__ __forceinline__ void prefetch_l2_line(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p) : "memory");
 }
-// fire-and-forget float add into global memory (L2 atomic unit; a shared-memory float atomic is a compare-and-swap
-// loop on this architecture)
-__device__ __forceinline__ void red_global_add_f32(float* p, float v) {
-    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+// fire-and-forget add into global memory (L2 atomic unit) of v in fixed point, mlp3_layout.h kGradFixShift: the sum does
+// not depend on the order in which CTAs arrive
+__device__ __forceinline__ void red_global_add_fixed(long long* p, float v) {
+    const long long q = __float2ll_rn(v * (float)(1ull << kGradFixShift));          // saturates; |v| < 128 in range
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(q) : "memory");
 }
 // 32 bytes (16 saved activations of one channel) in one request; the L2 is asked to fetch the surrounding 256 bytes
 struct H32 { uint4 a, b; };
@@ -148,11 +149,13 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
         };
         // chunk cc (0..3) of this thread's 64 points: 32 bytes, 8 KB apart (mlp3_layout.h, save3_offset)
         auto pair_off = [&](int cc, uint32_t) { return save3_offset(cc, 0); };
-        // L2 prefetch of the saved activations, three jobs ahead.  A job's 64 KB slice (mlp3_layout.h, Prog3Bwd::slice_off)
-        // is 16 pieces of 4 KB (128 channels x 32 B), one per point chunk, 8 KB apart: 512 lines, one per thread.
+        // L2 prefetch of the saved activations, three jobs ahead inside a group; the first three slices of the CTA's next
+        // group are requested when the current group's job loop ends (keeping "next group" out of the job loop's live
+        // registers: a spilled value costs a ~1000-cycle local-memory load per job).  A job's 64 KB slice
+        // (mlp3_layout.h, Prog3Bwd::slice_off) is 16 pieces of 4 KB (128 channels x 32 B), one per point chunk, 8 KB
+        // apart: 512 lines, one per thread.
         const uint32_t pf_thread = (uint32_t)e * 8192u + (uint32_t)lane * 128u;
-        auto prefetch_seq = [&](int g, int v) {      // v: index into [views, job 0 .. 17], may run over into the CTA's next group
-            if (v > kBwd3Jobs) { v -= kBwd3Jobs + 1; g = g + stride < prm.n_groups ? g + stride : g; }
+        auto prefetch_seq = [&](int g, int v) {      // v: index into [views, job 0 .. 17]
             prefetch_l2_line(prm.save + (size_t)g * kSave3GroupBytes + (pf_thread + prm.prog.slice_off[v]));
         };
         float2 c_next = make_float2(1.f, 0.f);
@@ -196,10 +199,10 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                     pa += __shfl_xor_sync(0xffffffffu, pa, o);
                 }
                 if (lane == 0) {
-                    red_global_add_f32(prm.grad_tmp + kChRgb + 0, pr);
-                    red_global_add_f32(prm.grad_tmp + kChRgb + 1, pgn);
-                    red_global_add_f32(prm.grad_tmp + kChRgb + 2, pb);
-                    red_global_add_f32(prm.grad_tmp + kChAlpha, pa);
+                    red_global_add_fixed(prm.grad_tmp + kChRgb + 0, pr);
+                    red_global_add_fixed(prm.grad_tmp + kChRgb + 1, pgn);
+                    red_global_add_fixed(prm.grad_tmp + kChRgb + 2, pb);
+                    red_global_add_fixed(prm.grad_tmp + kChAlpha, pa);
                 }
             }
             named_bar_sync3(1, 32 * kEpiWarps3);
@@ -222,10 +225,13 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
             }
             // 1/scale is read back from shared memory where it is needed (once per job): a register would be spilled to
             // local memory, whose loads take ~1000 cycles with the L1 carved out for shared memory
-            const uint32_t rinv_a = max_a + 8 + 4 * (it & 1);
+            // (one slot is enough: it is rewritten after the next group's first barrier, which every warp reaches only
+            // after its last job of this group)
+            const uint32_t rinv_a = max_a + 8;
             if (e == 8 && lane == 0) {
                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(max_a + 4 * ((it & 1) ^ 1)), "r"(0u) : "memory");
                 st_shared_f32(rinv_a, rinv);
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(max_a + 12), "r"(g) : "memory");      // group index for the job loop (same reason)
             }
             named_bar_sync3(1, 32 * kEpiWarps3);
 
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 }
                 // ds * s = sum dY (y - b) = s1 - b * (sum dY)
                 publish(kB3ActLo);
-                red_global_add_f32(prm.grad_tmp + kChViews + chh, (s1 - c.y * s2) * ld_shared_f32(rinv_a));
+                red_global_add_fixed(prm.grad_tmp + kChViews + chh, (s1 - c.y * s2) * ld_shared_f32(rinv_a));
             }
 
             // ================= dgrad chain =================
@@ -267,7 +273,8 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 const uint32_t hi = (f & JB_HI_HALF) ? 1u : 0u;
                 const uint32_t chh = 128u * hi + cl;                       // channel within the layer
                 const float2 c = c_next;
-                const uint8_t* hrow = saved_row(g, jb.slot, chh);
+                const int gj = ld_shared_s32(max_a + 12);           // == g, from shared memory instead of a spill slot
+                const uint8_t* hrow = saved_row(gj, jb.slot, chh);
                 const uint32_t row_addr = act + (chh >> 3) * kKGroup3 + pq * kNGroup3 + (chh & 7u) * 128u;
                 const uint32_t swz = (chh & 7u) << 4;
                 // saved activations: two chunks are requested before the accumulator is waited for, then each consumed
@@ -275,8 +282,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 H32 hh[2];
                 hh[0] = ldg_nc_32B(hrow + pair_off(0, swz));
                 hh[1] = ldg_nc_32B(hrow + pair_off(1, swz));
-                prefetch_seq(g, j + 3);            // the job after next, into L2 (one line per thread)
-                if (j == kBwd3Jobs - 1) prefetch_seq(g, j + 4);
+                if (j + 3 <= kBwd3Jobs) prefetch_seq(gj, j + 3);            // the job after next, into L2 (one line per thread)
                 unsigned long long tj0 = 0;
                 if (tracing) tj0 = clock64();
                 if (hi) { mbar_wait(bar(kB3AccReady + 1), ph_acc1); ph_acc1 ^= 1; }
@@ -323,8 +329,13 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                     chunk16(dpk, hp.a, hp.b, relu, write, row_addr, swz, cc, s1, s2);
                 }
                 if (write || hi) publish(hi ? kB3ActHi : kB3ActLo);
-                red_global_add_f32(prm.grad_tmp + jb.ch + cl, (s1 - c.y * s2) * ld_shared_f32(rinv_a));     // after the hand-over
+                red_global_add_fixed(prm.grad_tmp + jb.ch + cl, (s1 - c.y * s2) * ld_shared_f32(rinv_a));     // after the hand-over
                 if (tracing) t_job += clock64() - tj0;
+            }
+            if (g + stride < prm.n_groups) {
+                prefetch_seq(g + stride, 0);
+                prefetch_seq(g + stride, 1);
+                prefetch_seq(g + stride, 2);
             }
         }
         if (tracing && prm.dbg) {
@@ -341,13 +352,13 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
 
 // d_scale[i] += tmp[i] / s[i];  tmp[i] = 0  (the scratch is left zeroed for the next launch)
 __global__ void mlp3_backward_finalize_kernel(uint8_t* packed, float* __restrict__ d_scale) {
-    float* tmp = reinterpret_cast<float*>(packed + kOffGradTmp3);
+    long long* tmp = reinterpret_cast<long long*>(packed + kOffGradTmp3);
     const float* scale = reinterpret_cast<const float*>(packed + kOffScale);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < kNumChannels) {
-        const float v = tmp[i];
-        tmp[i] = 0.0f;
-        if (v != 0.0f) d_scale[i] += v / scale[i];
+        const long long q = tmp[i];
+        tmp[i] = 0;
+        if (q != 0) d_scale[i] += (float)((double)q * (1.0 / (double)(1ull << kGradFixShift))) / scale[i];
     }
 }
 
@@ -372,7 +383,7 @@ extern "C" int nerfq_mlp_backward(void* packed, const float* d_raw, const float*
     // the kernel accumulates s*ds into a scratch array of the packed buffer (zeroed by nerfq_pack_net and by every
     // finalize), the finalize kernel divides by the LSA scale and adds into d_scale
     uint8_t* pk = (uint8_t*)packed;
-    Bwd3Params prm{(const uint8_t*)packed, d_raw, raw, (const uint8_t*)save, reinterpret_cast<float*>(pk + kOffGradTmp3), n_points, n_groups,
+    Bwd3Params prm{(const uint8_t*)packed, d_raw, raw, (const uint8_t*)save, reinterpret_cast<long long*>(pk + kOffGradTmp3), n_points, n_groups,
                    g_trace3b, prog};
     if (g_trace3b) {
         if (cudaFuncSetAttribute(mlp3_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS3Bytes) != cudaSuccess) return -2;

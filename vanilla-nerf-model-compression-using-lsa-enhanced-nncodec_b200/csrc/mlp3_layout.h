@@ -238,8 +238,14 @@ constexpr size_t kOffBwd3Image = kOffFwd3Image + kFwd3ImageBytes;
 // The backward image holds W^T * (delta * lsa_scale) per output channel of W (the contraction index of the dgrad
 // GEMM), rebuilt by nerfq_set_scale_bias from the integer-level copy below, so that the backward epilogue hands the
 // masked gradient itself to the next GEMM instead of multiplying every element by the channel's scale.
-constexpr size_t kOffGradTmp3 = kOffBwd3Image + kBwd3ImageBytes;          // float[2440] backward scratch (kept zeroed)
-constexpr size_t kOffBwd3Levels = (kOffGradTmp3 + 4 * 2440 + 1023) / 1024 * 1024;     // backward image, integer levels
+// Backward scratch: long long[2440], kept zeroed.  The scale gradients are summed over CTAs and groups in FIXED POINT
+// (value * 2^kGradFixShift as a 64-bit integer, native L2 atomics): integer addition is associative, so the gradients --
+// and with the forward's fixed-point alpha head the whole LSA iteration -- are bit-reproducible, which float atomics
+// are not (measured 2e-4 of max run to run on heavily cancelling elements).  Range +-128, resolution 1.4e-17.
+constexpr int kGradFixShift = 56;
+constexpr size_t kGradTmp3Bytes = 8 * 2440;
+constexpr size_t kOffGradTmp3 = (kOffBwd3Image + kBwd3ImageBytes + 15) / 16 * 16;
+constexpr size_t kOffBwd3Levels = (kOffGradTmp3 + kGradTmp3Bytes + 1023) / 1024 * 1024;     // backward image, integer levels
 constexpr size_t kOffBwd3StageCh = kOffBwd3Levels + kBwd3ImageBytes;      // int[2 * kBwd3Chunks]: channel of k = 0 per stage
 constexpr size_t kPacked3Bytes = kOffBwd3StageCh + 4 * 2 * kBwd3Chunks;
 

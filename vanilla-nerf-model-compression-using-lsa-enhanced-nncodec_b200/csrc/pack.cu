@@ -174,7 +174,7 @@ extern "C" int nerfq_pack_net(void* packed, const void* const* weights12, const 
     for (int i = 0; i < kBwd3Steps; ++i) tabs.bwd[i] = kBwd3[i];
     pack_images3_kernel<<<2 * (kFwd3Chunks + kBwd3Chunks), 256, 0, stream>>>(p, tabs);
     pack_small_kernel<<<8, 256, 0, stream>>>(p);
-    cudaMemsetAsync(p.packed + kOffGradTmp3, 0, 4 * 2440, stream);
+    cudaMemsetAsync(p.packed + kOffGradTmp3, 0, kGradTmp3Bytes, stream);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 

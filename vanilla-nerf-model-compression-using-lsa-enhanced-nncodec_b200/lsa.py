@@ -73,9 +73,22 @@ class LSAStep:
         self.optimizer.step()
         return loss.detach()
 
+    def _init_optimizer_state(self):
+        """Create Adam's per-parameter state (step, exp_avg, exp_avg_sq) the way torch.optim.Adam does on its first
+        step().  Inside a capture that lazy initialisation would be RECORDED, and every replay would start from a fresh
+        optimizer; with the state created beforehand the graph only holds the update itself."""
+        for group in self.optimizer.param_groups:
+            for p in group["params"]:
+                st = self.optimizer.state[p]
+                if len(st) == 0:
+                    st["step"] = torch.zeros((), dtype=torch.float32, device=p.device)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+
     def capture(self, warmup: int = 3):
         """Record the iteration in a CUDA graph (after `warmup` eager iterations on a side stream, which also update
-        the parameters).  Raises if anything on the path is not capturable; the eager `step` stays usable."""
+        the parameters; 0 is allowed).  Raises if anything on the path is not capturable; the eager `step` stays usable."""
+        self._init_optimizer_state()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
