@@ -227,3 +227,36 @@ def test_deepcabac_front_end_matches_oracle(dev):
         deepcabac.Decoder().dequantLayer(rec, quantized, 2, qp, 0)
         assert (rec == qo.dequant(lv_ref, used_ref, 2)).all(), name
         assert np.abs(rec - values).max() <= 0.5 * qo.stepsize(qp, 2) * (1 + 1e-6)
+
+
+def test_c_abi_error_codes_and_empty_inputs(dev):
+    """include/nerfq.h contract, called through ctypes exactly as a foreign host would: 0 on success and on empty inputs
+    (nothing launched, pointers not dereferenced), -1 on bad arguments; no exception crosses the ABI."""
+    import ctypes as C
+    ops = _ops()
+    L = ops.L()
+    null, stream = C.c_void_p(0), C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    buf = torch.zeros(64, dtype=torch.float32, device=dev)
+    ibuf = torch.zeros(64, dtype=torch.int32, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    # empty inputs
+    assert L.nerfq_quantize_urq(null, null, C.c_longlong(0), -20, 2, null, null, stream) == 0
+    assert L.nerfq_dequantize(null, null, C.c_longlong(0), -20, 2, stream) == 0
+    assert L.nerfq_mlp_forward(null, null, null, C.c_longlong(0), 64, null, null, 0, stream) == 0
+    assert L.nerfq_mlp_backward(null, null, null, null, C.c_longlong(0), null, 0, stream) == 0
+    assert int(L.nerfq_mlp_save_bytes(C.c_longlong(0))) == 0
+    # bad arguments
+    assert L.nerfq_quantize_urq(null, p(ibuf), C.c_longlong(8), -20, 2, null, p(ibuf), stream) == -1          # no input
+    assert L.nerfq_quantize_urq(p(buf), p(ibuf), C.c_longlong(-1), -20, 2, null, p(ibuf), stream) == -1      # negative size
+    assert L.nerfq_quantize_urq(p(buf), p(ibuf), C.c_longlong(8), -20, 9, null, p(ibuf), stream) == -1       # qp_density out of range
+    assert L.nerfq_dequantize(p(ibuf), null, C.c_longlong(8), -20, 2, stream) == -1
+    assert L.nerfq_mlp_forward(null, p(buf), p(buf), C.c_longlong(4), 64, p(buf), null, 0, stream) == -1      # no packed network
+    assert L.nerfq_mlp_forward(p(buf), p(buf), p(buf), C.c_longlong(4), 0, p(buf), null, 0, stream) == -1     # samples_per_ray <= 0
+    assert L.nerfq_mlp_backward(p(buf), null, p(buf), p(buf), C.c_longlong(4), p(buf), 0, stream) == -1
+    out = C.c_float()
+    assert L.nerfq_stepsize(-20, 2, C.byref(out)) == 0 and out.value == 2.0 ** -5
+    assert L.nerfq_stepsize(-20, 9, C.byref(out)) == -1
+    torch.cuda.synchronize()
+    # a save buffer sized by the library covers whole 256-point groups, ten 128 KB slots each
+    assert int(L.nerfq_mlp_save_bytes(C.c_longlong(1))) == 10 * 131072
+    assert int(L.nerfq_mlp_save_bytes(C.c_longlong(257))) == 2 * 10 * 131072
