@@ -32,6 +32,9 @@ QP, QP_DENSITY, NONWEIGHT_QP = -20, 2, -75
 FLOP_PER_POINT_FWD = 2 * 593408
 FLOP_PER_POINT_BWD = 2 * 557696
 METRIC = "rays/sec render_rays (64+128 samples/ray); LSA steps/sec"
+# the same workload name in both arms (this implementation and --impl reference)
+WORKLOAD = ("cfg2: LSA fine-tuning step at qp=-20 (quantise -> LSA-scaled dequant -> render 4096 rays/GPU, 64+128 samples -> "
+            "backward into LSA scales -> Adam), random-init vanilla NeRF, synthetic rays")
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 4096 rays x 192 samples (profiles/)
 NCU_DRAM_BYTES = {"mlp_bwd_fine": 3917792000 + 13829888, "mlp_fwd_fine": 4663552 + 3803394000}      # profiles/r01_ncu_mlp_kernels_summary.txt
 
@@ -164,8 +167,9 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": sec * 1e3 * RAYS_PER_GPU / sample, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "lsa_steps_per_sec": rays_s / RAYS_PER_GPU,
-            "config": {"workload": "cfg2: LSA step qp=-20, 64+128 samples, random-init vanilla NeRF (CPU oracle port of the reference)",
-                       "rays_per_step_sample": sample, "rays_per_step_full": RAYS_PER_GPU},
+            "config": {"workload": WORKLOAD, "rays_per_gpu": RAYS_PER_GPU, "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE, "qp": QP,
+                       "perturb": 1.0, "white_bkgd": True, "implementation": "CPU oracle port of the reference (stock torch fp32)",
+                       "rays_per_step_sample": sample},
             "cpu_baseline": {"value": rays_s, "unit": "rays/s", "cores": threads, "kind": "port",
                              "sample": f"{sample}-ray LSA steps (fwd+bwd+Adam), torch CPU fp32, mean of {args.steps}"},
             "e2e": {"value": rays_s, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -290,8 +294,7 @@ def run_cuda(args):
                 "lsa_steps_per_sec": 1e3 / ms_step,
                 "lsa_steps_per_sec_no_requant": 1e3 / ms_norequant,
                 "render_rays_per_sec_forward_only": world * n_view / (ms_view * 1e-3),
-                "config": {"workload": "cfg2: LSA fine-tuning step at qp=-20 (quantise -> LSA-scaled dequant in the MLP epilogue -> "
-                                       "render 4096 rays/GPU, 64+128 samples -> backward into LSA scales -> Adam)",
+                "config": {"workload": WORKLOAD,
                            "rays_per_gpu": RAYS_PER_GPU, "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE, "qp": QP,
                            "perturb": 1.0, "white_bkgd": True, "requantize_every_step": requant_each_step, "cuda_graph": graphed,
                            "operands": "fp16 operands, fp32 accumulate (TMEM)",
