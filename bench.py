@@ -266,6 +266,21 @@ def run_cuda(args):
             R.render(4, 4, None, chunk=32768, rays=(ov, dv), near=2.0, far=6.0, **test_kw)
     ms_view = timed(fwd_only, max(3, args.steps // 2), 3)
 
+    # (3b) BASELINE cfg3: one 800x800 view from a camera pose (rays generated on the device, 20 chunks of 32768 rays),
+    # rows sharded over the ranks as distributed.render_view_sharded does
+    H = W = 800
+    f_cam = 0.5 * W / np.tan(0.5 * 0.6911112070083618)          # nerf_synthetic camera_angle_x (load_blender.py:71-72)
+    K_cam = np.array([[f_cam, 0, 0.5 * W], [0, f_cam, 0.5 * H], [0, 0, 1]], dtype=np.float32)
+    c2w = np.array([[1, 0, 0, 0.0], [0, 0.8660254, 0.5, 2.0], [0, -0.5, 0.8660254, 3.4641016]], dtype=np.float32)
+    lo, hi = (H * W * rank) // world, (H * W * (rank + 1)) // world
+    view_kw = {k: v for k, v in test_kw.items() if k not in ("use_viewdirs", "network_query_fn", "ndc", "near", "far")}
+
+    def view_cfg3():
+        with torch.no_grad():
+            rays = ops.camera_rays(H, W, K_cam, c2w, False, 2.0, 6.0, dev, first_pixel=lo, count=hi - lo)
+            R.batchify_rays(rays, 32768, **view_kw)
+    ms_cfg3 = timed(view_cfg3, 3, 2)
+
     # (4) kernel-level timing for the roofline (live CUDA events around single launches, same sizes as the step)
     kern = {}
     if rank == 0:
@@ -294,6 +309,7 @@ def run_cuda(args):
                 "lsa_steps_per_sec": 1e3 / ms_step,
                 "lsa_steps_per_sec_no_requant": 1e3 / ms_norequant,
                 "render_rays_per_sec_forward_only": world * n_view / (ms_view * 1e-3),
+                "render_view_800x800_ms": ms_cfg3,
                 "config": {"workload": WORKLOAD,
                            "rays_per_gpu": RAYS_PER_GPU, "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE, "qp": QP,
                            "perturb": 1.0, "white_bkgd": True, "requantize_every_step": requant_each_step, "cuda_graph": graphed,

@@ -98,8 +98,17 @@ class LSAStep:
         torch.cuda.current_stream(self.device).wait_stream(side)
         self.optimizer.zero_grad(set_to_none=True)        # backward() then allocates .grad inside the graph's pool
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            self.loss = self.step(self.rays, self.target)
+        # The parameters' AccumulateGrad nodes were created on whatever stream first ran a backward; the capture stream
+        # differs from it by construction, which autograd reports once per process.  The capture orders the streams itself.
+        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if quiet is not None:
+            quiet(False)
+        try:
+            with torch.cuda.graph(graph):
+                self.loss = self.step(self.rays, self.target)
+        finally:
+            if quiet is not None:
+                quiet(True)
         self.graph = graph
         return self
 
