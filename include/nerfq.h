@@ -73,7 +73,8 @@ int nerfq_set_scale_bias(void* packed, const float* scale, const float* bias, ne
  * The sample points o + d*z, their positional encodings and all layer activations stay on chip; operands are fp16
  * (weights: exact integer levels), accumulation is fp32, the epilogue applies delta*scale and bias in fp32.
  * save (nullable): nerfq_mlp_save_bytes(n_rays*S) bytes receiving the activations the backward needs.
- * max_ctas: 0 = one CTA per SM.
+ * max_ctas: 0 = one CTA per SM.  The result does not depend on max_ctas, on how the rays are split over calls, or on
+ * the run: partial sums that meet in arbitrary order are accumulated in fixed point.
  * ---------------------------------------------------------------------------------------------- */
 int nerfq_mlp_forward(const void* packed, const float* rays, const float* z, long long n_rays, int samples_per_ray,
                       float* raw, void* save, int max_ctas, nerfq_stream_t stream);
@@ -81,9 +82,9 @@ unsigned long long nerfq_mlp_save_bytes(long long n_points);
 
 /* Gradient of the loss w.r.t. the LSA scales (replaces torch autograd over NeRF.forward with only
  * weight_scaling trainable: framework/pytorch_model/__init__.py:1129-1145, run_nerf.py:756).
- * d_scale [2436] is ACCUMULATED (caller zeroes).  `packed` is not const: a 10 KB scratch area inside it holds the
- * partial sums of the launch (left zeroed again on completion), so one packed network must not run two backward
- * launches concurrently. */
+ * d_scale [2436] is ACCUMULATED (caller zeroes).  `packed` is not const: a 19.5 KB scratch area inside it holds the
+ * partial sums of the launch as 64-bit fixed point (left zeroed again on completion), so one packed network must not
+ * run two backward launches concurrently.  The sums are order-independent: the result is bit-reproducible. */
 int nerfq_mlp_backward(void* packed, const float* d_raw, const float* raw, const void* save, long long n_points,
                        float* d_scale, int max_ctas, nerfq_stream_t stream);
 
