@@ -45,6 +45,14 @@ def test_cfg2_size_shard_and_chunk_invariance(dev, wrapper):
         assert torch.equal(full[k], again[k])
         assert torch.equal(full[k], chunked[k])
         assert torch.equal(full[k], torch.cat([s[k] for s in shards], 0))
+    # ... nor on how many CTAs share the work
+    R.TUNING["max_ctas"] = 37
+    try:
+        with torch.no_grad():
+            few = R.render(4, 4, None, chunk=32768, rays=rays, near=2.0, far=6.0, retraw=True, **kw)
+    finally:
+        R.TUNING["max_ctas"] = 0
+    assert torch.equal(full[0], few[0]) and torch.equal(full[3]["raw"], few[3]["raw"])
     rgb, disp, acc, ex = full
     assert torch.isfinite(rgb).all() and float(rgb.min()) >= 0.0 and float(rgb.max()) <= 1.0 + 1e-5
     assert float(acc.min()) >= 0.0 and float(acc.max()) <= 1.0 + 1e-5
