@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import golden
+from tests.util import golden, synth_rays
 
 pytestmark = pytest.mark.gpu
 
@@ -260,3 +260,41 @@ def test_c_abi_error_codes_and_empty_inputs(dev):
     # a save buffer sized by the library covers whole 256-point groups, ten 128 KB slots each
     assert int(L.nerfq_mlp_save_bytes(C.c_longlong(1))) == 10 * 131072
     assert int(L.nerfq_mlp_save_bytes(C.c_longlong(257))) == 2 * 10 * 131072
+
+
+def test_mlp_kernels_stay_inside_their_buffers(dev):
+    """Ragged sizes (37 rays x 33 samples = 1221 points = 4.77 groups of 256) through the C ABI with sentinel-filled
+    guard regions behind every output buffer: raw, the saved activations and d_scale are written only inside their
+    documented extents, and the ragged tail computes the same values as a padded run."""
+    import ctypes as C
+    from nerfq_b200 import codec, model as nmodel, packed
+    ops = _ops()
+    L = ops.L()
+    torch.manual_seed(5)
+    w = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params().to(dev)
+    codec.quantize_model(w, -20)
+    pn = w.model_fine.packed_net()
+    pn.set_scales(w.model_fine.scale_tensors())
+    n, S = 37, 33
+    r = synth_rays(n, 31).to(dev)
+    z = torch.sort(2.0 + 4.0 * torch.rand(n, S, device=dev), -1).values.contiguous()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    guard = 4096
+    raw = torch.full((n * S * 4 + guard,), 777.0, device=dev)
+    save_bytes = packed.mlp_save_bytes(n * S)
+    assert save_bytes == 5 * 10 * 131072
+    save = torch.full((save_bytes + guard,), 0x5A, dtype=torch.uint8, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    assert L.nerfq_mlp_forward(C.c_void_p(pn.ptr), p(r), p(z), C.c_longlong(n), S, p(raw), p(save), 0, stream) == 0
+    torch.cuda.synchronize()
+    assert (raw[n * S * 4:] == 777.0).all() and torch.isfinite(raw[:n * S * 4]).all()
+    assert (save[save_bytes:] == 0x5A).all()
+    ref = packed.mlp_forward(pn, r, z)                       # same call without save through the Python wrapper
+    assert torch.equal(ref.reshape(-1), raw[:n * S * 4])
+    d_raw = torch.randn(n * S * 4, device=dev) * 1e-4
+    d_scale = torch.full((2436 + guard,), 0.0, device=dev)
+    d_scale[2436:] = 777.0
+    assert L.nerfq_mlp_backward(C.c_void_p(pn.ptr), p(d_raw), p(raw), p(save), C.c_longlong(n * S), p(d_scale), 0, stream) == 0
+    torch.cuda.synchronize()
+    assert (d_scale[2436:] == 777.0).all() and torch.isfinite(d_scale[:2436]).all() and float(d_scale[:2436].abs().max()) > 0
+    assert (save[save_bytes:] == 0x5A).all() and (raw[n * S * 4:] == 777.0).all()
