@@ -346,6 +346,12 @@ def run_cuda(args):
                 sec, threads = cpu_lsa_steps(oracle_model(), sample, 3, 1)
                 line["cpu_baseline"] = {"value": sample / sec, "unit": "rays/s", "cores": threads, "kind": "port",
                                         "sample": f"{sample}-ray LSA steps (fwd+bwd+Adam) of the oracle, torch CPU fp32, mean of 3 after 1 warm-up"}
+                # what tune_model itself runs with (torch.set_num_threads(1), framework/pytorch_model/__init__.py:1088)
+                torch.set_num_threads(1)
+                sec1, _ = cpu_lsa_steps(oracle_model(), 256, 2, 1)
+                line["cpu_baseline_1thread"] = {"value": 256 / sec1, "unit": "rays/s", "cores": 1, "kind": "port",
+                                                "sample": "256-ray LSA steps of the oracle, torch CPU fp32, mean of 2 after 1 warm-up"}
+                torch.set_num_threads(os.cpu_count() or 1)
             except Exception as ex:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": "rays/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
             # secondary comparison: the same stock-torch code on this GPU, full 4096-ray steps
