@@ -89,6 +89,57 @@ __global__ void __launch_bounds__(128, 1) probe2_kernel(const uint16_t* A, const
     if (warp == 0) tmem_dealloc2(tmem, 256);
 }
 
+// Second configuration ("points on lanes"): A = activations [256 points][64 k], K-major SWIZZLE_128B, each CTA holds ITS
+// 128 rows; B = weights [256 channels][64 k] as two K-major SWIZZLE_64B stages of [128 rows][32 k], each CTA holds ITS
+// 128 rows.  Expected: CTA r receives D rows 128 r .. (its points) x all 256 columns, column n = weight row n.
+__global__ void __launch_bounds__(128, 1) probe2k_kernel(const uint16_t* A, const uint16_t* B, float* D) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t rank = cluster_ctarank();
+    const int tid = threadIdx.x, warp = tid >> 5;
+    constexpr uint32_t kA = 0, kB = 16384, kBars = 32768, kTptr = kBars + 64;
+    auto bar = [&](int i) { return sbase + kBars + 8u * i; };
+    for (int ch = 0; ch < 8; ++ch) {          // A: one SWIZZLE_128B block [128 rows][128 B]
+        const uint4 q = *reinterpret_cast<const uint4*>(A + (size_t)(128 * rank + tid) * 64 + ch * 8);
+        *reinterpret_cast<uint4*>(smem + kA + sw128_offset(tid, ch)) = q;
+    }
+    for (int st = 0; st < 2; ++st)
+        for (int ch = 0; ch < 4; ++ch) {
+            const uint4 q = *reinterpret_cast<const uint4*>(B + (size_t)(128 * rank + tid) * 64 + st * 32 + ch * 8);
+            *reinterpret_cast<uint4*>(smem + kB + st * 8192 + sw64_offset(tid, ch)) = q;
+        }
+    if (tid == 0) { mbar_init(bar(0), 1); mbar_init(bar(1), 8); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc2(sbase + kTptr, 256);
+    fence_proxy_async_all();
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after_sync();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + kTptr);
+    if (rank == 0 && warp == 0) {
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc(256, 256, false);
+            const uint64_t a0 = umma_smem_desc(sbase + kA, 1024, SWZ_128B), b0 = umma_smem_desc(sbase + kB, 512, SWZ_64B);
+            for (int j = 0; j < 4; ++j)
+                umma_ss2(tmem, a0 + ((j * 32) >> 4), b0 + (((j >> 1) * 8192 + (j & 1) * 32) >> 4), idesc, j ? 1u : 0u);
+            umma_commit2_mc(bar(0), 3);
+        }
+        __syncwarp();
+    }
+    mbar_wait(bar(0), 0);
+    tc_fence_after_sync();
+    for (int c = 0; c < 256; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+        tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) D[(size_t)(128 * rank + tid) * 256 + c + i] = __uint_as_float(v[i]);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) tmem_dealloc2(tmem, 256);
+}
+
 static uint16_t h16(float f) { __half h = __float2half(f); uint16_t u; memcpy(&u, &h, 2); return u; }
 
 int main() {
@@ -126,6 +177,30 @@ int main() {
         printf("cta_group::2 M=256 N=256 K=64, operand tile written %s: %s (%d mismatches%s)\n", remote ? "by the peer CTA (DSMEM)" : "locally",
                bad ? "FAIL" : "PASS", bad, bad ? "" : "");
         if (bad) { printf("  first mismatch at o=%d n=%d: got %g\n", first / 256, first % 256, D[first]); ++fails; }
+    }
+    {
+        cudaFuncSetAttribute(probe2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaMemset(dD, 0, 256 * 256 * 4);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t err = cudaLaunchKernelEx(&cfg, probe2k_kernel, (const uint16_t*)dA, (const uint16_t*)dB, dD);
+        if (err == cudaSuccess) err = cudaDeviceSynchronize();
+        if (err != cudaSuccess) { printf("K-major/K-major: CUDA error %s\n", cudaGetErrorString(err)); return 1; }
+        std::vector<float> D(256 * 256);
+        cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+        int bad = 0, first = -1;
+        for (int m = 0; m < 256; ++m)
+            for (int n = 0; n < 256; ++n) {
+                float ref = 0;
+                for (int k = 0; k < 64; ++k) ref += Af[m * 64 + k] * Bf[n * 64 + k];
+                if (D[m * 256 + n] != ref) { if (first < 0) first = m * 256 + n; ++bad; }
+            }
+        printf("cta_group::2 M=256 N=256 K=64, A K-major SW128 (points) x B K-major SW64 (weights): %s (%d mismatches)\n", bad ? "FAIL" : "PASS", bad);
+        if (bad) { printf("  first mismatch at m=%d n=%d: got %g\n", first / 256, first % 256, D[first]); ++fails; }
     }
     return fails ? 1 : 0;
 }

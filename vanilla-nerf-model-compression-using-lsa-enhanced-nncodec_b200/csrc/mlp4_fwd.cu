@@ -443,7 +443,8 @@ static unsigned long long* g_trace4 = nullptr;
 // wait operand; epilogue warp 5: wait accumulator, job, hand-over} from the tracing instantiation.
 extern "C" void nerfq_mlp4_set_trace(unsigned long long* buf) { g_trace4 = buf; }
 
-// The single-CTA kernel (mlp3_fwd.cu) is the default; NERFQ_MLP_FWD=4 selects the pair schedule.  Measured on B200
+// The single-CTA kernel (mlp3_fwd.cu) is the default; NERFQ_MLP_FWD=4 selects this pair schedule, NERFQ_MLP_FWD=5 the
+// points-on-lanes pair schedule of mlp5_fwd.cu for calls without `save` (both experiments, both slower).  Measured on B200
 // (profiles/r01_mlp4_pair_schedule_trace.log): results identical, but 1.53 ms against 0.85 ms -- the operand rows that
 // cross the pair (32 KB per layer and group each way) move at distributed-shared-memory speed, and the cluster-scope
 // release that hands them over compiles to a GPU-scope MEMBAR: ~2.0 k cycles per hand-over and 2.6 k per epilogue job
@@ -453,7 +454,9 @@ extern "C" int nerfq_mlp_forward(const void* packed, const float* rays, const fl
     using namespace nerfq;
     if (n_rays == 0) return 0;
     if (!packed || !rays || !z || !raw || n_rays < 0 || samples_per_ray <= 0) return -1;
-    static const int use_v4 = [] { const char* e = getenv("NERFQ_MLP_FWD"); return e && e[0] == '4'; }();
+    static const int which = [] { const char* e = getenv("NERFQ_MLP_FWD"); return e ? e[0] - '0' : 0; }();
+    if (which == 5 && !save && !mlp3_forward_tracing()) return mlp5_forward_launch(packed, rays, z, n_rays, samples_per_ray, raw, max_ctas, stream);
+    const bool use_v4 = which == 4;
     if (!use_v4 || mlp3_forward_tracing()) return mlp3_forward_launch(packed, rays, z, n_rays, samples_per_ray, raw, save, max_ctas, stream);
     static const Prog4Fwd prog = make_prog4_fwd();
     const long long n_points = n_rays * samples_per_ray;
