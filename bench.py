@@ -18,7 +18,6 @@ import sys
 import threading
 import time
 
-os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 
 import numpy as np
 import torch

@@ -32,7 +32,9 @@ typedef struct CUstream_st* nerfq_stream_t; /* == cudaStream_t */
 int nerfq_stepsize(int qp, int qp_density, float* out);
 
 /* level = sign(w) * (int)(|w|/delta + 0.5f).  The qp is raised until the largest level fits int32
- * (baseline.py:60-62) and written to *qp_used (device int, nullable).  workspace4: 4 bytes. */
+ * (baseline.py:60-62) and written to *qp_used (device int, nullable).  workspace4: 4 bytes.
+ * Non-finite input never hangs or traps: a NaN / Inf element gets level 0, and when the tensor's maximum is
+ * non-finite the qp is left as requested (the clip search is bounded). */
 int nerfq_quantize_urq(const float* w, int32_t* lvl, long long n, int qp, int qp_density, int* qp_used,
                        void* workspace4, nerfq_stream_t stream);
 
@@ -57,9 +59,17 @@ unsigned long long nerfq_packed_net_bytes(void);
 int nerfq_num_channels(void);
 
 /* weights12: HOST array of 12 device pointers ([out,in] row-major; int32 levels if src_is_int32 else float32);
- * delta12: HOST array of the 12 step sizes (1.0 for unquantised weights). */
+ * delta12: HOST array of the 12 step sizes (1.0 for unquantised weights).
+ * Operand range: the MLP kernels multiply fp16 operands.  Integer levels up to +-2048 are exact; larger ones are rounded
+ * to 11 significant bits (relative error <= 2^-12) and, beyond fp16's range, a power of two is folded into the layer's
+ * delta so nothing overflows.  Float weights are normalised per layer by a power of two the same way. */
 int nerfq_pack_net(void* packed, const void* const* weights12, const float* delta12, int src_is_int32,
                    nerfq_stream_t stream);
+
+/* max |level| (or |weight|) of each of the 12 layers as found by the last nerfq_pack_net, copied to max_abs12
+ * (DEVICE float[12]): > 2048 for an int32 source means that layer's operands were rounded; NaN / Inf means the
+ * source held non-finite values. */
+int nerfq_pack_status(const void* packed, float* max_abs12, nerfq_stream_t stream);
 
 /* Epilogue constants {delta*scale, bias} per output channel; scale == NULL means no LSA (scale 1).  Must follow every
  * nerfq_pack_net and every change of the scales: it also rebuilds the backward weight image (level * delta * scale,
@@ -84,7 +94,9 @@ unsigned long long nerfq_mlp_save_bytes(long long n_points);
  * weight_scaling trainable: framework/pytorch_model/__init__.py:1129-1145, run_nerf.py:756).
  * d_scale [2436] is ACCUMULATED (caller zeroes).  `packed` is not const: a 19.5 KB scratch area inside it holds the
  * partial sums of the launch as 64-bit fixed point (left zeroed again on completion), so one packed network must not
- * run two backward launches concurrently.  The sums are order-independent: the result is bit-reproducible. */
+ * run two backward launches concurrently.  The sums are order-independent: the result is bit-reproducible.
+ * Ranges: a per-channel sum s*ds beyond +-32768 saturates (2^-48 fixed point); a channel whose LSA scale is exactly 0
+ * reports gradient 0 (the kernel recovers sum dY (W x) from y - b = s (W x), which vanishes with s). */
 int nerfq_mlp_backward(void* packed, const float* d_raw, const float* raw, const void* save, long long n_points,
                        float* d_scale, int max_ctas, nerfq_stream_t stream);
 

@@ -30,12 +30,14 @@ float nncq_stepsize(int qp, int qp_density)
  * overflow".  Restated as: smallest qp' >= qp whose largest level fits in int32. */
 int nncq_clip_qp(float max_abs, int qp, int qp_density)
 {
-    for (;;) {
+    if (!(max_abs <= 3.402823466e+38f)) return qp;   /* NaN / Inf maximum: qp as requested (our convention, no reference) */
+    for (int it = 0; it < 1024; ++it) {
         float d = nncq_stepsize(qp, qp_density);
         float q = max_abs / d + 0.5f;
         if (q < 2147483648.0f) return qp;
         ++qp;
     }
+    return qp;
 }
 
 /* baseline.py:48-57 (dq_flag = 0): w float32 -> int32 levels, row-major scan (scan_order 0).
@@ -45,15 +47,17 @@ int nncq_quant_urq(const float *w, int32_t *lvl, int64_t n, int qp, int qp_densi
     float max_abs = 0.0f;
     for (int64_t i = 0; i < n; ++i) {
         float a = fabsf(w[i]);
-        if (a > max_abs) max_abs = a;
+        if (a > max_abs || a != a) max_abs = a;      /* NaN sticks, like the bit-pattern maximum of the GPU kernel */
+        if (max_abs != max_abs) break;
     }
     int qp_used = nncq_clip_qp(max_abs, qp, qp_density);
     float d = nncq_stepsize(qp_used, qp_density);
     for (int64_t i = 0; i < n; ++i) {
         float a = fabsf(w[i]);
+        if (!(a <= 3.402823466e+38f)) { lvl[i] = 0; continue; }     /* NaN / Inf -> level 0 (our convention) */
         volatile float q = a / d;        /* keep the fp32 rounding of the quotient */
         volatile float r = q + 0.5f;
-        int32_t m = (int32_t)r;
+        int32_t m = r >= 2147483648.0f ? 2147483647 : (int32_t)r;
         lvl[i] = (w[i] < 0.0f) ? -m : m;
     }
     return qp_used;

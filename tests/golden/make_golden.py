@@ -57,6 +57,73 @@ def build_model():
     return model
 
 
+def build_model_trained():
+    """A 'trained-like' NeRFWrapper + LSA at qp=-38 (delta 1.46e-3): what a real checkpoint does to the fused path
+    that a random-init net does not -- quantisation levels beyond 2048 (not exact as fp16 operands) and densities in
+    the hundreds.  A random MLP with large weights is a chaotic function (the reference then disagrees with ITSELF by
+    more than the gate under fp32 re-association), so the large levels are introduced through ReLU homogeneity:
+    pts_linears.{2,4,6} get weight and bias x64/x80/x100 (levels up to 2731/3413/4267) and the following layer's LSA
+    scale is divided by the same factor -- the function stays the smooth random-init field.  alpha_linear x50 (levels to
+    2133) with bias 0.7 gives sigma ~0.9..1.0 (weights spread over many samples); the `dense` variant uses x60 and bias
+    150 (sigma ~150: saturated alphas, the fixed-point sigma sum far from zero).  rgb_linear x8 for colour contrast."""
+    torch.manual_seed(11)
+    wrapper = ref.utils.NeRFWrapper()
+    model = ref.transforms.LSA(wrapper).add_lsa_params()
+    delta = np.float32(stepsize(-38, 2))
+    g = torch.Generator().manual_seed(4321)
+    store = {"delta": np.float32(delta)}
+    with torch.no_grad():
+        for net in ("model", "model_fine"):
+            for lname in LAYERS:
+                mod = model.get_submodule(f"{net}.{lname}")
+                mod.weight_scaling.copy_(1.0 + 0.05 * torch.randn(mod.weight_scaling.shape, generator=g))
+            for li, c in ((6, 100.0), (2, 64.0), (4, 80.0)):
+                a = model.get_submodule(f"{net}.pts_linears.{li}")
+                b = model.get_submodule(f"{net}.pts_linears.{li + 1}")
+                a.weight.mul_(c); a.bias.mul_(c); b.weight_scaling.mul_(1.0 / c)
+            model.get_submodule(f"{net}.rgb_linear").weight.mul_(8.0)
+            al = model.get_submodule(f"{net}.alpha_linear")
+            base = al.weight.clone()
+            lv_dense = torch.round(base * 60.0 / float(delta))
+            store[f"{net}.alpha_linear.levels_dense"] = lv_dense.numpy().astype(np.int16)
+            al.weight.copy_(base * 50.0)
+            al.bias.add_(0.7)
+            for lname in LAYERS:
+                mod = model.get_submodule(f"{net}.{lname}")
+                lv = torch.round(mod.weight / float(delta))
+                assert float(lv.abs().max()) < 32767
+                mod.weight.copy_(lv * float(delta))
+                key = f"{net}.{lname}"
+                store[key + ".levels"] = lv.numpy().astype(np.int16)
+                store[key + ".bias"] = mod.bias.numpy().copy()
+                store[key + ".weight_scaling"] = mod.weight_scaling.numpy().copy()
+    store["dense_alpha_bias_shift"] = np.float32(150.0 - 0.7)
+    np.savez_compressed(os.path.join(HERE, "model_trained_qm38.npz"), **store)
+    return model, delta, store
+
+
+def case_render_trained():
+    """run_nerf.render (run_nerf.py:81-158) on the trained-like model, both alpha variants, 64+128 samples."""
+    model, delta, store = build_model_trained()
+    o, d = synth_rays(160, 21)
+    out = {"rays_o": np_(o), "rays_d": np_(d)}
+    for variant in ("spread", "dense"):
+        if variant == "dense":
+            with torch.no_grad():
+                for net in ("model", "model_fine"):
+                    al = model.get_submodule(f"{net}.alpha_linear")
+                    al.weight.copy_(torch.from_numpy(store[f"{net}.alpha_linear.levels_dense"].astype(np.float32)) * float(delta))
+                    al.bias.add_(float(store["dense_alpha_bias_shift"]))
+        with torch.no_grad():
+            rgb, disp, acc, ex = ref.run_nerf.render(4, 4, None, chunk=80, rays=(o, d), near=2.0, far=6.0, ndc=False,
+                                                     retraw=True, **render_kwargs(model))
+        out.update({f"{variant}_rgb": np_(rgb), f"{variant}_disp": np_(disp), f"{variant}_acc": np_(acc),
+                    f"{variant}_rgb0": np_(ex["rgb0"]), f"{variant}_acc0": np_(ex["acc0"]), f"{variant}_disp0": np_(ex["disp0"]),
+                    f"{variant}_z_std": np_(ex["z_std"]), f"{variant}_sigma_minmax": np.array([float(ex["raw"][..., 3].min()),
+                                                                                             float(ex["raw"][..., 3].max())], dtype=np.float32)})
+    np.savez_compressed(os.path.join(HERE, "render_trained.npz"), **out)
+
+
 def synth_rays(n, seed, near=2.0, far=6.0):
     g = torch.Generator().manual_seed(seed)
     o = 0.1 * torch.randn(n, 3, generator=g) + torch.tensor([0.0, 0.0, 4.0])
@@ -208,6 +275,7 @@ if __name__ == "__main__":
     case_functions()
     case_lsa_step(m)
     case_stepsize()
+    case_render_trained()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -4,7 +4,7 @@ import torch
 
 import nerfq_b200  # noqa: F401
 from nerfq_b200 import model as nmodel
-from tests.util import LAYERS, NETS, golden_model_levels, golden_model_params
+from tests.util import LAYERS, NETS, golden_model_levels, golden_model_params, golden_trained_params
 
 
 def golden_wrapper(dev, with_levels: bool):
@@ -19,6 +19,16 @@ def golden_wrapper(dev, with_levels: bool):
     if with_levels:
         for net in NETS:
             m = getattr(w, net)
-            m.quant_levels = [torch.from_numpy(levels[f"{net}.{l}"]).to(dev) for l in LAYERS]
-            m.quant_steps = [delta] * 12
+            m.set_quant_levels([torch.from_numpy(levels[f"{net}.{l}"]).to(dev) for l in LAYERS], [delta] * 12)
+    return w, p
+
+
+def trained_wrapper(dev, variant="spread"):
+    """Our NeRFWrapper+LSA carrying the trained-like fixture (qp=-38, levels beyond 2048) with its integer levels attached."""
+    p, levels, delta = golden_trained_params(variant)
+    w = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params()
+    w.load_state_dict({k: v.reshape(-1, 1) if k.endswith("weight_scaling") else v for k, v in p.items()})
+    w = w.to(dev)
+    for net in NETS:
+        getattr(w, net).set_quant_levels([torch.from_numpy(levels[f"{net}.{l}"]).to(dev) for l in LAYERS], [delta] * 12)
     return w, p

@@ -1,0 +1,212 @@
+"""GPU parity tests added in round 2: operand-range handling (levels beyond 2048, densities in the hundreds, non-finite
+input), oracle parity at the BASELINE cfg2 size, the LLFF sampling configuration (N_importance=64, NDC) and lindisp,
+every qp of the cfg5 sweep, and stale-level invalidation.  Gate (north_star): rgb/disp/acc within 1e-3 absolute;
+integer levels bit-exact."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from tests.test_gpu_render import GATE, disp_err, maxerr
+from tests.util import LAYERS, NETS, golden, synth_rays
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("variant", ["spread", "dense"])
+def test_render_trained_like_golden(dev, variant):
+    """Trained-like fixture from the unmodified reference: qp=-38, levels up to 4267 (rounded to 11 bits as fp16 operands),
+    sigma ~1 ('spread') or ~150 ('dense').  The packer reports the range; the render stays inside the gate."""
+    from nerfq_b200 import packed, render as R
+    from tests.gpu_util import trained_wrapper
+    g = golden("render_trained.npz")
+    w, _ = trained_wrapper(dev, variant)
+    _, test_kw = R.create_nerf(w, white_bkgd=True, dataset_type="blender")
+    rays = (torch.from_numpy(g["rays_o"]).to(dev), torch.from_numpy(g["rays_d"]).to(dev))
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        with torch.no_grad():
+            rgb, disp, acc, ex = R.render(4, 4, None, chunk=80, rays=rays, near=2.0, far=6.0, retraw=True, **test_kw)
+    assert any("not exact fp16" in str(r.message) for r in rec)          # the caller is told
+    mx = w.model_fine.packed_net().max_abs_per_layer()
+    assert mx[6] == 4267.0 and mx[2] > 2048 and mx[1] < 100
+    assert maxerr(rgb, g[variant + "_rgb"]) < GATE and maxerr(acc, g[variant + "_acc"]) < GATE
+    assert disp_err(disp, g[variant + "_disp"]) < GATE
+    assert maxerr(ex["rgb0"], g[variant + "_rgb0"]) < GATE and maxerr(ex["acc0"], g[variant + "_acc0"]) < GATE
+    assert maxerr(ex["z_std"], g[variant + "_z_std"]) < GATE
+    lo, hi = g[variant + "_sigma_minmax"]
+    sg = ex["raw"][..., 3]
+    assert abs(float(sg.max()) - hi) < 2e-2 * max(1.0, hi) and abs(float(sg.min()) - lo) < 2e-2 * max(1.0, abs(lo))
+    # strict policy refuses inexact operands instead of warning
+    old = packed.LEVEL_RANGE_POLICY
+    packed.LEVEL_RANGE_POLICY = "raise"
+    try:
+        w.model_fine._packed = None
+        with pytest.raises(packed.LevelRangeError):
+            w.model_fine.packed_net()
+    finally:
+        packed.LEVEL_RANGE_POLICY = old
+
+
+def test_pack_handles_levels_beyond_fp16_range(dev):
+    """Levels above 65504 (qp far below the tested sweep) must not become inf: a power of two moves from the operands into
+    the layer's delta.  Checked through run_network against the float reference of the same layer stack."""
+    from nerfq_b200 import model as nmodel, packed, render as R
+    from oracle import render_oracle as ro
+    torch.manual_seed(2)
+    w = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params().to(dev)
+    delta = 2.0 ** -22                                       # |w| ~ 0.06 -> levels ~ 2.6e5
+    net = w.model_fine
+    levels = [torch.round(l.weight.detach() / delta).to(torch.int32) for l in net.layers()]
+    with torch.no_grad():
+        for l, lv in zip(net.layers(), levels):
+            l.weight.copy_(lv.float() * delta)
+    net.set_quant_levels(levels, [delta] * 12)
+    old = packed.LEVEL_RANGE_POLICY
+    packed.LEVEL_RANGE_POLICY = "ignore"
+    try:
+        gen = torch.Generator().manual_seed(3)
+        pts = torch.randn(4, 9, 3, generator=gen)
+        vd = torch.nn.functional.normalize(torch.randn(4, 3, generator=gen), dim=-1)
+        raw = R.run_network(pts.to(dev), vd.to(dev), net)
+        assert max(net.packed_net().max_abs_per_layer()) > 65504
+    finally:
+        packed.LEVEL_RANGE_POLICY = old
+    p = {k: (v.detach().cpu().reshape(-1) if k.endswith("weight_scaling") else v.detach().cpu()) for k, v in w.state_dict().items()}
+    with torch.no_grad():
+        ref = ro.query_network(p, "model_fine", pts, vd)
+    assert torch.isfinite(raw).all() and maxerr(raw, ref) < 5e-3
+
+
+def test_cfg2_size_oracle_parity(dev):
+    """BASELINE configs[1] at full size: 4096 rays, 64+128 samples, forward outputs, loss and all 24 scale gradients
+    against the CPU oracle (perturb=0 so both sides see the same samples)."""
+    from nerfq_b200 import render as R
+    from oracle import render_oracle as ro
+    from tests.gpu_util import golden_wrapper
+    from tests.test_gpu_lsa import _check, _grads
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    w, p = golden_wrapper(dev, True)
+    for name, prm in w.named_parameters():
+        prm.requires_grad_(name.endswith("weight_scaling"))
+    kw, _ = R.create_nerf(w, perturb=0.0, white_bkgd=True)
+    kw.pop("use_viewdirs"); kw.pop("ndc"); kw.pop("lindisp")
+    n = 4096
+    batch = synth_rays(n, 2)
+    target = torch.rand(n, 3, generator=torch.Generator().manual_seed(3))
+    grads_ref = {}
+    loss_ref = 0.0
+    outs = []
+    for i in range(0, n, 1024):                              # the oracle in slices (memory); the loss is a mean over all 4096
+        l, gr, out = ro.lsa_scale_grads(p, batch[i:i + 1024], target[i:i + 1024], white_bkgd=True)
+        loss_ref += l / 4
+        outs.append(out)
+        for k, v in gr.items():
+            grads_ref[k] = grads_ref.get(k, 0) + v / 4
+    out = R.render_rays(batch.to(dev), **kw)
+    loss = R.img2mse(out["rgb_map"], target.to(dev)) + R.img2mse(out["rgb0"], target.to(dev))
+    loss.backward()
+    for k in ("rgb_map", "acc_map", "rgb0", "acc0", "z_std"):
+        assert maxerr(out[k], torch.cat([o[k] for o in outs])) < GATE, k
+    assert disp_err(out["disp_map"], torch.cat([o["disp_map"] for o in outs]).numpy()) < GATE
+    assert abs(float(loss.detach()) - loss_ref) < 1e-4
+    _check(_grads(w), lambda k: grads_ref[k].numpy())
+
+
+def test_llff_configuration_ni64_ndc_and_lindisp(dev):
+    """The reference's LLFF setting (train_nerf.py:56-70: N_importance=64, NDC rays from a camera pose, near 0, far 1) and
+    the lindisp=True depth spacing (run_nerf.py:381-384) against the oracle, end to end."""
+    from nerfq_b200 import render as R
+    from oracle import render_oracle as ro
+    from tests.gpu_util import golden_wrapper
+    w, p = golden_wrapper(dev, True)
+    H, W, focal = 18, 24, 21.0
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]], dtype=np.float32)
+    c2w = torch.tensor([[0.98, 0.05, -0.19, 0.3], [-0.03, 0.99, 0.10, -0.2], [0.19, -0.09, 0.97, 0.1]])
+    _, kw = R.create_nerf(w, N_importance=64, white_bkgd=False, dataset_type="llff")
+    assert "ndc" not in kw and "lindisp" not in kw            # create_nerf leaves both at render()'s defaults for llff
+    with torch.no_grad():
+        rgb, disp, acc, ex = R.render(H, W, K, chunk=128, c2w=c2w, ndc=True, near=0.0, far=1.0, **kw)
+        r_rgb, r_disp, r_acc, r_ex = ro.render(p, H, W, K, chunk=128, c2w=c2w, ndc=True, near=0.0, far=1.0, n_importance=64, white_bkgd=False)
+    assert rgb.shape == (H, W, 3)
+    assert maxerr(rgb, r_rgb) < GATE and maxerr(acc, r_acc) < GATE and disp_err(disp, r_disp.numpy()) < GATE
+    assert maxerr(ex["rgb0"], r_ex["rgb0"]) < GATE and maxerr(ex["z_std"], r_ex["z_std"]) < GATE
+    # lindisp on un-warped rays (no_ndc LLFF / blender with lindisp), N_importance=64
+    _, kw = R.create_nerf(w, N_importance=64, white_bkgd=True, dataset_type="llff", no_ndc=True, lindisp=True)
+    assert kw["lindisp"] is True and kw["ndc"] is False
+    batch = synth_rays(300, 8, near=0.5, far=6.0)
+    rays = (batch[:, :3].contiguous().to(dev), batch[:, 3:6].contiguous().to(dev))
+    with torch.no_grad():
+        rgb, disp, acc, ex = R.render(4, 4, None, chunk=128, rays=rays, near=0.5, far=6.0, **kw)
+        ref = ro.render_rays(p, batch, n_importance=64, white_bkgd=True, lindisp=True)
+    assert maxerr(rgb, ref["rgb_map"]) < GATE and maxerr(acc, ref["acc_map"]) < GATE and disp_err(disp, ref["disp_map"].numpy()) < GATE
+    assert maxerr(ex["rgb0"], ref["rgb0"]) < GATE and maxerr(ex["z_std"], ref["z_std"]) < GATE
+
+
+def test_every_qp_of_the_sweep_bit_exact(dev):
+    """BASELINE cfg5: for EVERY qp in -38..-10 the levels of every tensor of the wrapper (24 weights at qp, 24 biases at
+    -75) from the batched GPU quantiser equal the host restatement, and the reconstructed values equal level*delta."""
+    from nerfq_b200 import codec, model as nmodel
+    from oracle import quant_oracle as qo
+    torch.manual_seed(0)
+    base = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params()
+    master = {k: v.detach().clone() for k, v in base.state_dict().items()}
+    w = base.to(dev)
+    for qp in range(-38, -9):
+        w.load_state_dict(master)
+        lv = codec.quantize_model(w, qp)
+        sd = w.state_dict()
+        for net in NETS:
+            for i, l in enumerate(LAYERS):
+                for kind, q in (("weight", qp), ("bias", -75)):
+                    ref, used = qo.quant_urq(master[f"{net}.{l}.{kind}"].numpy(), q, 2)
+                    assert used == q
+                    got = lv[net][f"{i}.{kind}"].cpu().numpy()
+                    assert (got == ref).all(), (qp, net, l, kind)
+                    assert (sd[f"{net}.{l}.{kind}"].cpu().numpy() == qo.dequant(ref, q, 2)).all(), (qp, net, l, kind)
+
+
+def test_quantizer_non_finite_input_terminates(dev):
+    """NaN / Inf must not spin the clip search.  Non-finite elements get level 0, finite ones quantise as usual,
+    the qp stays as requested; same convention as the C restatement."""
+    from nerfq_b200 import deepcabac, ops
+    from oracle import quant_oracle as qo
+    for bad in (np.nan, np.inf, -np.inf):
+        w = np.array([0.3, bad, -0.7, 1e-3, 2.5], dtype=np.float32)
+        lv, used = ops.quantize_urq(torch.from_numpy(w).to(dev), -20, 2)
+        ref, used_ref = qo.quant_urq(w, -20, 2)
+        torch.cuda.synchronize()
+        assert int(used.item()) == used_ref == -20
+        assert (lv.cpu().numpy() == ref).all() and ref[1] == 0 and ref[0] == 10
+        lvb, usedb = ops.quantize_batch([torch.from_numpy(w).to(dev)], [-20], 2)
+        assert (lvb[0].cpu().numpy() == ref).all() and int(usedb[0]) == -20
+        out = np.zeros(w.shape, dtype=np.int32)
+        assert deepcabac.Encoder().quantLayer(w, out, 0, 2, -20, 0.0, 10, 0) == -20 and (out == ref).all()
+
+
+def test_stale_levels_are_dropped_when_weights_change(dev):
+    """after codec.quantize_model a later load_state_dict / in-place weight update must reach the renderer."""
+    from nerfq_b200 import codec, model as nmodel, render as R
+    torch.manual_seed(1)
+    w = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params().to(dev)
+    other = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params().to(dev)
+    codec.quantize_model(w, -20)
+    assert w.model_fine.quant_levels is not None
+    r = synth_rays(64, 3).to(dev)
+    rays = (r[:, :3].contiguous(), r[:, 3:6].contiguous())
+    _, kw = R.create_nerf(w, white_bkgd=True)
+    with torch.no_grad():
+        a = R.render(4, 4, None, rays=rays, near=2.0, far=6.0, **kw)[0]
+        assert w.model_fine.quant_levels is not None              # untouched weights keep their levels
+        w.load_state_dict(other.state_dict())
+        b = R.render(4, 4, None, rays=rays, near=2.0, far=6.0, **kw)[0]
+        assert w.model_fine.quant_levels is None and w.model.quant_levels is None
+        _, kwo = R.create_nerf(other, white_bkgd=True)
+        c = R.render(4, 4, None, rays=rays, near=2.0, far=6.0, **kwo)[0]
+    assert torch.equal(b, c) and not torch.equal(a, b)

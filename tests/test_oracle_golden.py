@@ -121,3 +121,19 @@ def test_quant_c_vs_numpy_and_roundtrip():
     big = np.array([3e4, -1.0], dtype=np.float32)       # |w|/delta(-75) > 2^31 -> qp is raised
     lv, used = quant_oracle.quant_urq(big, -75, 2)
     assert used > -75 and abs(int(lv[0])) < 2 ** 31
+
+
+def test_render_trained_like():
+    """The trained-like fixture (qp=-38, levels to 4267, both alpha variants) through the oracle restatement."""
+    from tests.util import golden_trained_params
+    g = golden("render_trained.npz")
+    rays = (torch.from_numpy(g["rays_o"][:48]), torch.from_numpy(g["rays_d"][:48]))
+    for variant in ("spread", "dense"):
+        p, levels, _ = golden_trained_params(variant)
+        assert max(int(np.abs(v).max()) for v in levels.values()) > 4000
+        with torch.no_grad():
+            rgb, disp, acc, ex = ro.render(p, 4, 4, None, chunk=48, rays=rays, ndc=False, near=2.0, far=6.0, white_bkgd=True, retraw=True)
+        close(rgb, g[variant + "_rgb"][:48]); close(acc, g[variant + "_acc"][:48]); close(disp, g[variant + "_disp"][:48], nan_ok=True)
+        close(ex["rgb0"], g[variant + "_rgb0"][:48]); close(ex["z_std"], g[variant + "_z_std"][:48])
+        lo, hi = g[variant + "_sigma_minmax"]
+        assert (hi > 100.0) == (variant == "dense")

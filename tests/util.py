@@ -43,3 +43,24 @@ def synth_rays(n, seed, near=2.0, far=6.0):
     d = -d / torch.norm(d, dim=-1, keepdim=True)
     vd = d / torch.norm(d, dim=-1, keepdim=True)
     return torch.cat([o, d, near * torch.ones(n, 1), far * torch.ones(n, 1), vd], -1)
+
+
+def golden_trained_params(variant="spread"):
+    """The trained-like fixture model of make_golden.py::build_model_trained at qp=-38: returns (state-dict style float
+    params, {layer: int32 levels}, delta).  variant 'dense' swaps in the alpha head with densities around 150."""
+    z = golden("model_trained_qm38.npz")
+    delta = np.float32(z["delta"])
+    p, levels = {}, {}
+    for net in NETS:
+        for l in LAYERS:
+            k = f"{net}.{l}"
+            lv = z[k + ".levels"].astype(np.int32)
+            bias = z[k + ".bias"].copy()
+            if variant == "dense" and l == "alpha_linear":
+                lv = z[k + ".levels_dense"].astype(np.int32)
+                bias = bias + np.float32(z["dense_alpha_bias_shift"])
+            levels[k] = lv
+            p[k + ".weight"] = torch.from_numpy(lv.astype(np.float32) * delta)
+            p[k + ".bias"] = torch.from_numpy(bias)
+            p[k + ".weight_scaling"] = torch.from_numpy(z[k + ".weight_scaling"])
+    return p, levels, float(delta)

@@ -13,6 +13,7 @@ _PROTOS = {
     "nerfq_packed_net_bytes": (c_ull, []),
     "nerfq_num_channels": (c_int, []),
     "nerfq_pack_net": (c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_float), c_int, c_void_p]),
+    "nerfq_pack_status": (c_int, [c_void_p, c_void_p, c_void_p]),
     "nerfq_set_scale_bias": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "nerfq_mlp_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "nerfq_mlp_save_bytes": (c_ull, [c_ll]),

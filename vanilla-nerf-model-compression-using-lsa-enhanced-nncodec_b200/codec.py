@@ -38,8 +38,9 @@ def _quantize_nets(nets, qp: int, qp_density: int, nonweight_qp: int):
             out[f"{i}.weight"], out[f"{i}.bias"] = outs[k], outs[k + 1]
             levels.append(outs[k])
             k += 2
-        net.quant_levels, net.quant_steps = levels, [step] * 12
-        net._packed = None         # (the kernel wrote through raw pointers: torch version counters did not move)
+        # (the kernel wrote level*delta through raw pointers: torch's version counters did not move, so the key taken
+        # here describes exactly the reconstructed weights)
+        net.set_quant_levels(levels, [step] * 12)
         res.append(out)
     return res
 
@@ -85,6 +86,5 @@ def apply_lsa(wrapper):
             value = value * ls.reshape([-1] + [1] * (value.dim() - 1)) if ls is not None else value
         dst[name].copy_(value)
     for net in (out.model, out.model_fine):
-        net.quant_levels = None
-        net._packed = None
+        net.set_quant_levels(None, None)
     return out

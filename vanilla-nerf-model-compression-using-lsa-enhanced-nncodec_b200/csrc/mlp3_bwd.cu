@@ -46,7 +46,7 @@ __device__ __forceinline__ void prefetch_l2_line(const void* p) {
 // fire-and-forget add into global memory (L2 atomic unit) of v in fixed point, mlp3_layout.h kGradFixShift: the sum does
 // not depend on the order in which CTAs arrive
 __device__ __forceinline__ void red_global_add_fixed(long long* p, float v) {
-    const long long q = __float2ll_rn(v * (float)(1ull << kGradFixShift));          // saturates; |v| < 128 in range
+    const long long q = __float2ll_rn(v * (float)(1ull << kGradFixShift));          // saturates; |v| < 32768 in range
     asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(q) : "memory");
 }
 // 32 bytes (16 saved activations of one channel) in one request; the L2 is asked to fetch the surrounding 256 bytes
@@ -350,7 +350,9 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-// d_scale[i] += tmp[i] / s[i];  tmp[i] = 0  (the scratch is left zeroed for the next launch)
+// d_scale[i] += tmp[i] / s[i];  tmp[i] = 0  (the scratch is left zeroed for the next launch).
+// A scale of exactly 0 makes y - b = 0, so the kernel cannot recover sum dY (L x) delta from its saved activations:
+// that channel's gradient is reported as 0 (finite) instead of 0/0 -- documented in include/nerfq.h.
 __global__ void mlp3_backward_finalize_kernel(uint8_t* packed, float* __restrict__ d_scale) {
     long long* tmp = reinterpret_cast<long long*>(packed + kOffGradTmp3);
     const float* scale = reinterpret_cast<const float*>(packed + kOffScale);
@@ -358,7 +360,8 @@ __global__ void mlp3_backward_finalize_kernel(uint8_t* packed, float* __restrict
     if (i < kNumChannels) {
         const long long q = tmp[i];
         tmp[i] = 0;
-        if (q != 0) d_scale[i] += (float)((double)q * (1.0 / (double)(1ull << kGradFixShift))) / scale[i];
+        const float sc = scale[i];
+        if (q != 0 && sc != 0.0f) d_scale[i] += (float)((double)q * (1.0 / (double)(1ull << kGradFixShift))) / sc;
     }
 }
 

@@ -24,7 +24,6 @@
 #include <cuda_runtime.h>
 
 #include "mlp3_common.cuh"
-#include "mlp4_fwd.h"
 
 namespace nerfq {
 
@@ -42,6 +41,7 @@ struct Fwd3Params {
     Prog3Fwd prog;
 };
 
+constexpr float kAlphaFix = 262144.0f;       // 2^18: fixed-point unit of the alpha-head sum (int32: +-8192 logit units)
 constexpr int kSaveInJob = 2;      // chunks (of 4) whose saved activations are stored from registers inside the job; measured 1: 1.04, 2: 0.97, 3: 0.99, 4: 1.04 ms
 
 template <bool kSave, bool kTrace>
@@ -107,9 +107,9 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
             c = make_float2(0.f, 0.f);
             wa = 0.0f;
             if (!(jn.flags & JB_FINAL)) c = __ldg(&g_sb[jn.ch + 32 * q + lane]);
-            // alpha head weight of this channel as fixed-point logit units: level * (delta*scale of the head) * 2^20
+            // alpha head weight of this channel as fixed-point logit units: level * (delta*scale of the head) * kAlphaFix
             if (jn.flags & JB_ALPHA)
-                wa = __ldg(&g_wa[((jn.flags & JB_HI_HALF) ? 128 : 0) + 32 * q + lane]) * __ldg(&g_sb[kChAlpha]).x * 1048576.0f;
+                wa = __ldg(&g_wa[((jn.flags & JB_HI_HALF) ? 128 : 0) + 32 * q + lane]) * __ldg(&g_sb[kChAlpha]).x * kAlphaFix;
         };
 
         float2 c_next = make_float2(0.f, 0.f);
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                                 }
                             }
                             const int pl = pq * 64 + cc * 32 + lane;
-                            const float sg = fmaf((float)ld_shared_s32(out_sa + 4 * pl), 1.0f / 1048576.0f, ca.y);      // exact: |sum| < 2^24 logit-2^-20 units
+                            const float sg = fmaf((float)ld_shared_s32(out_sa + 4 * pl), 1.0f / kAlphaFix, ca.y);
                             st_shared_f32(out_sa + 4 * pl, 0.0f);
                             const long long gi = g0 + cc * 32 + lane;
                             if (gi < prm.n_points) prm.raw[4 * gi + 3] = sg;
@@ -212,11 +212,12 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                     if (kSave && cc < kSaveInJob) st_global_v8(save_ch + save3_offset(pq * 4 + cc, 0), pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
                     if (f & JB_ALPHA) {
                         // Alpha head over this warp's 32 channels (L7 is a ReLU layer: the head sees max(y, 0)), in fixed
-                        // point: each term  max(y,0) * level * (delta*scale) of the sigma logit is rounded to 2^-20, the
+                        // point: each term  max(y,0) * level * (delta*scale) of the sigma logit is rounded to 2^-18, the
                         // warp sum is one REDUX per point, and the eight partial sums of a point (4 warps x 2 halves) meet
                         // in native integer shared-memory atomics.  Integer addition is associative, so sigma -- and with it
                         // every pixel -- is bit-reproducible (a float butterfly + float atomics, a compare-and-swap loop
-                        // on sm_100, cost the same and were not).  Range +-2048 logit units, rounding error < 4e-6 rms.
+                        // on sm_100, cost the same and were not).  Range +-8192 logit units (kAlphaFix; two's-complement partial
+                        // sums may wrap, only the total must fit), rounding error 1.8e-5 rms over the 256 terms.
                         int sum[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) sum[i] = __reduce_add_sync(0xffffffffu, __float2int_rn(fmaxf(y[i], 0.0f) * wa));
@@ -286,11 +287,8 @@ static int g_trace3_flags = 0;
 // writes 8 cycle counters per CTA into this device buffer (see profiles/trace_v3.py).
 extern "C" void nerfq_mlp_set_trace(unsigned long long* buf, int flags) { g_trace3 = buf; g_trace3_flags = flags; }
 
-bool nerfq::mlp3_forward_tracing() { return g_trace3 != nullptr; }
-
-// The single-CTA schedule; nerfq_mlp_forward (mlp4_fwd.cu) dispatches here for A/B measurements and tracing.
-int nerfq::mlp3_forward_launch(const void* packed, const float* rays, const float* z, long long n_rays, int samples_per_ray,
-                               float* raw, void* save, int max_ctas, cudaStream_t stream) {
+extern "C" int nerfq_mlp_forward(const void* packed, const float* rays, const float* z, long long n_rays, int samples_per_ray,
+                                  float* raw, void* save, int max_ctas, cudaStream_t stream) {
     using namespace nerfq;
     if (n_rays == 0) return 0;
     if (!packed || !rays || !z || !raw || n_rays < 0 || samples_per_ray <= 0) return -1;

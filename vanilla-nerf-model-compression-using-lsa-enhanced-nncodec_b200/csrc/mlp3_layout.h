@@ -241,8 +241,9 @@ constexpr size_t kOffBwd3Image = kOffFwd3Image + kFwd3ImageBytes;
 // Backward scratch: long long[2440], kept zeroed.  The scale gradients are summed over CTAs and groups in FIXED POINT
 // (value * 2^kGradFixShift as a 64-bit integer, native L2 atomics): integer addition is associative, so the gradients --
 // and with the forward's fixed-point alpha head the whole LSA iteration -- are bit-reproducible, which float atomics
-// are not (measured 2e-4 of max run to run on heavily cancelling elements).  Range +-128, resolution 1.4e-17.
-constexpr int kGradFixShift = 56;
+// are not (measured 2e-4 of max run to run on heavily cancelling elements).  Range +-32768 (the conversion saturates
+// beyond it), resolution 3.6e-15: gradients of a mean-squared loss are 1e-7..1e-3, a summed loss still fits.
+constexpr int kGradFixShift = 48;
 constexpr size_t kGradTmp3Bytes = 8 * 2440;
 constexpr size_t kOffGradTmp3 = (kOffBwd3Image + kBwd3ImageBytes + 15) / 16 * 16;
 constexpr size_t kOffBwd3Levels = (kOffGradTmp3 + kGradTmp3Bytes + 1023) / 1024 * 1024;     // backward image, integer levels

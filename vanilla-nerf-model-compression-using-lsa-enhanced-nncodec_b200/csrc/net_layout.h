@@ -30,13 +30,14 @@ constexpr int kLayerCh[kNumLayers] = {0, 256, 512, 768, 1024, 1280, 1536, 1792, 
 
 // ---- packed network buffer, small fields (the weight images follow, see mlp3_layout.h) ----------
 // [ sb: float2{delta*lsa_scale, bias}[2436] | delta[2436] | lsa_scale[2436] | w_alpha float[256] (levels) |
-//   w_rgb float[3*128] (levels) ]
+//   w_rgb float[3*128] (levels) | layer_max float[16] ]
 constexpr size_t kOffSB = 0;
 constexpr size_t kOffDelta = kOffSB + sizeof(float) * 2 * kNumChannels;
 constexpr size_t kOffScale = kOffDelta + sizeof(float) * kNumChannels;
 constexpr size_t kOffWAlpha = kOffScale + sizeof(float) * kNumChannels;
 constexpr size_t kOffWRgb = kOffWAlpha + sizeof(float) * 256;
-constexpr size_t kPackedBytesRaw = kOffWRgb + sizeof(float) * 384;
+constexpr size_t kOffLayerMax = kOffWRgb + sizeof(float) * 384;        // float bits: max |level| (or |weight|) per layer, nerfq_pack_status
+constexpr size_t kPackedBytesRaw = kOffLayerMax + sizeof(float) * 16;
 constexpr size_t kPackedBytes = (kPackedBytesRaw + 255) / 256 * 256;
 
 static_assert(kOffSB % 16 == 0, "alignment");

@@ -5,8 +5,19 @@
 // The reference keeps, per Linear layer, a float32 `weight` that holds dequantised values
 // level*delta (nnc_core/approximator/baseline.py:73-101 feeding framework/pytorch_model/__init__.py:
 // 1093-1111) and a `weight_scaling` [out,1] (transforms.py:94).  Here the integer levels themselves are
-// the tensor-core operands (exact in fp16 up to |level| <= 2048) and delta*scale is applied in the
-// epilogue, so dequantisation never materialises a float weight tensor.
+// the tensor-core operands and delta*scale is applied in the epilogue, so dequantisation never materialises
+// a float weight tensor.
+//
+// Operand range (fp16: 11-bit significand, max 65504).  Per layer the largest |value| is reduced first
+// (layer_absmax_kernel) and a power of two 2^k is folded out of the operands and into the layer's delta
+// (exact: a power of two changes no significand):
+//   integer levels:  k = 0 while max|level| < 2^15, so levels up to 2048 are EXACT operands (qp -20 on a
+//                    random-init net: <= 100); between 2049 and 65504 a level is rounded to 11 significant bits
+//                    (relative error <= 2^-12, the rounding any fp16 weight gets); beyond, k > 0 keeps it finite.
+//   float weights:   k = exponent(max) - 10, i.e. the layer's largest weight lands in [1024, 2048): small weights
+//                    stay normal fp16 numbers instead of sinking into the subnormals.
+// max|value| per layer is kept in the packed buffer and returned by nerfq_pack_status, so the host can tell the
+// caller when the "exact integer operand" property does not hold (packed.PackedNet warns or raises).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -27,9 +38,35 @@ __device__ __constant__ int kInDev[kNumLayers] = {63, 256, 256, 256, 256, 319, 2
 __device__ __constant__ int kOutDev[kNumLayers] = {256, 256, 256, 256, 256, 256, 256, 256, 1, 256, 128, 3};
 __device__ __constant__ int kChDev[kNumLayers] = {0, 256, 512, 768, 1024, 1280, 1536, 1792, kChAlpha, kChFeature, kChViews, kChRgb};
 
-__device__ __forceinline__ float load_w(const PackParams& p, int layer, int idx) {
-    return p.src_is_int32 ? (float)reinterpret_cast<const int32_t*>(p.w[layer])[idx]
-                          : reinterpret_cast<const float*>(p.w[layer])[idx];
+// max |value| of each layer as float bits (non-negative floats order like unsigned ints); NaN / Inf sort above
+// every finite value and are reported as they are
+__global__ void layer_absmax_kernel(const PackParams p) {
+    const int layer = blockIdx.y;
+    const int n = kOutDev[layer] * kInDev[layer];
+    unsigned int m = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float v = p.src_is_int32 ? (float)reinterpret_cast<const int32_t*>(p.w[layer])[i]
+                                       : reinterpret_cast<const float*>(p.w[layer])[i];
+        m = max(m, __float_as_uint(fabsf(v)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(reinterpret_cast<unsigned int*>(p.packed + kOffLayerMax) + layer, m);
+}
+
+// the power of two folded out of a layer's operands (see the header): returns 2^-k, the factor applied to the values
+__device__ __forceinline__ float operand_factor(const PackParams& p, int layer) {
+    const unsigned int bits = reinterpret_cast<const unsigned int*>(p.packed + kOffLayerMax)[layer];
+    const int ex = (int)((bits >> 23) & 0xff) - 127;          // floor(log2(max)); -127 for zero / subnormal
+    if (bits == 0 || ex == 128) return 1.0f;                   // empty or non-finite layer: leave it alone
+    int k = p.src_is_int32 ? max(0, ex - 14) : ex - 10;
+    k = max(-100, min(100, k));
+    return __int_as_float((127 - k) << 23);
+}
+
+__device__ __forceinline__ float load_w(const PackParams& p, int layer, int idx, float factor) {
+    return factor * (p.src_is_int32 ? (float)reinterpret_cast<const int32_t*>(p.w[layer])[idx]
+                                    : reinterpret_cast<const float*>(p.w[layer])[idx]);
 }
 
 // ---- weight images ("channels on lanes", mlp3_layout.h): stages of [128 rows x 32 k] in consumption order
@@ -57,6 +94,7 @@ __global__ void pack_images3_kernel(const PackParams p, const Step3Tables tabs) 
     const int per_half = st.kh + st.kp;
     const int mh = sidx / per_half, j = sidx % per_half;
     const int in = kInDev[st.layer], out = kOutDev[st.layer];
+    const float factor = operand_factor(p, st.layer);
     if (bwd && threadIdx.x == 0)        // the stage's 32 contraction indices are output channels 32 j .. of this layer
         reinterpret_cast<int*>(p.packed + kOffBwd3StageCh)[stage] = kChDev[st.layer] + 32 * j;
     for (int item = threadIdx.x; item < 128 * 4; item += blockDim.x) {
@@ -81,11 +119,11 @@ __global__ void pack_images3_kernel(const PackParams p, const Step3Tables tabs) 
                         col = st.pcol0 + kk;
                     }
                 }
-                if (o < out && col >= 0) x = load_w(p, st.layer, o * in + col);
+                if (o < out && col >= 0) x = load_w(p, st.layer, o * in + col, factor);
             } else {
                 // backward: A[r][kk] = W[o = 32 j + kk][hcol0 + 128 mh + r]
                 const int o = j * 32 + chunk * 8 + e;
-                if (o < st.hvalid && o < out) x = load_w(p, st.layer, o * in + st.hcol0 + 128 * mh + r);
+                if (o < st.hvalid && o < out) x = load_w(p, st.layer, o * in + st.hcol0 + 128 * mh + r, factor);
             }
             v[e] = x;
         }
@@ -105,11 +143,11 @@ __global__ void pack_small_kernel(const PackParams p) {
             int layer = 0;
             for (int l = 0; l < kNumLayers; ++l)
                 if (i >= kChDev[l] && i < kChDev[l] + kOutDev[l]) layer = l;
-            delta[i] = p.delta[layer];
+            delta[i] = p.delta[layer] / operand_factor(p, layer);          // delta * 2^k
         } else if (i < kNumChannels + 256) {
-            wa[i - kNumChannels] = load_w(p, 8, i - kNumChannels);
+            wa[i - kNumChannels] = load_w(p, 8, i - kNumChannels, operand_factor(p, 8));
         } else {
-            wr[i - kNumChannels - 256] = load_w(p, 11, i - kNumChannels - 256);
+            wr[i - kNumChannels - 256] = load_w(p, 11, i - kNumChannels - 256, operand_factor(p, 11));
         }
     }
 }
@@ -172,10 +210,19 @@ extern "C" int nerfq_pack_net(void* packed, const void* const* weights12, const 
     Step3Tables tabs;
     for (int i = 0; i < kFwd3Steps; ++i) tabs.fwd[i] = kFwd3[i];
     for (int i = 0; i < kBwd3Steps; ++i) tabs.bwd[i] = kBwd3[i];
+    cudaMemsetAsync(p.packed + kOffLayerMax, 0, 4 * kNumLayers, stream);
+    layer_absmax_kernel<<<dim3(8, kNumLayers), 256, 0, stream>>>(p);
     pack_images3_kernel<<<2 * (kFwd3Chunks + kBwd3Chunks), 256, 0, stream>>>(p, tabs);
     pack_small_kernel<<<8, 256, 0, stream>>>(p);
     cudaMemsetAsync(p.packed + kOffGradTmp3, 0, kGradTmp3Bytes, stream);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+extern "C" int nerfq_pack_status(const void* packed, float* max_abs12, cudaStream_t stream) {
+    using namespace nerfq;
+    if (!packed || !max_abs12) return -1;
+    return cudaMemcpyAsync(max_abs12, reinterpret_cast<const uint8_t*>(packed) + kOffLayerMax, 4 * kNumLayers, cudaMemcpyDeviceToDevice,
+                           stream) == cudaSuccess ? 0 : -3;
 }
 
 extern "C" int nerfq_set_scale_bias(void* packed, const float* scale, const float* bias, cudaStream_t stream) {

@@ -333,15 +333,16 @@ __device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, 
     asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3) : "memory");
 }
-// {lo, hi} -> packed fp16 pair, round to nearest; the relu form clamps negative inputs to +0 in the same instruction
+// {lo, hi} -> packed fp16 pair, round to nearest, saturating at +-65504 instead of producing inf (one F2FP either way);
+// the relu form clamps negative inputs to +0 in the same instruction
 __device__ __forceinline__ uint32_t cvt_pack_f16(float lo, float hi) {
     uint32_t d;
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
     return d;
 }
 __device__ __forceinline__ uint32_t cvt_pack_f16_relu(float lo, float hi) {
     uint32_t d;
-    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
     return d;
 }
 

@@ -18,8 +18,13 @@ __host__ __device__ inline float stepsize(int qp, int qp_density) {
     return ldexpf((float)mul, shift);
 }
 
+// Non-finite input (a diverged LSA scale, a corrupt tensor): a NaN / Inf maximum leaves the qp as requested and the
+// non-finite elements get level 0 (to_level); the search is bounded -- the step size doubles every 2^qp_density steps, so
+// FLT_MAX / delta drops below 2^31 long before kMaxClipSteps.
+constexpr int kMaxClipSteps = 1024;
 __host__ __device__ inline int clip_qp(float max_abs, int qp, int qp_density) {
-    for (;;) {
+    if (!(max_abs <= 3.402823466e+38f)) return qp;
+    for (int it = 0; it < kMaxClipSteps; ++it) {
         const float d = stepsize(qp, qp_density);
 #ifdef __CUDA_ARCH__
         const float q = __fadd_rn(__fdiv_rn(max_abs, d), 0.5f);
@@ -30,6 +35,16 @@ __host__ __device__ inline int clip_qp(float max_abs, int qp, int qp_density) {
         if (q < 2147483648.0f) return qp;
         ++qp;
     }
+    return qp;
+}
+
+// level of one value: nearest integer of |x| / d, ties away from zero; NaN / Inf -> 0; saturates at INT32_MAX
+__device__ __forceinline__ int to_level(float x, float d) {
+    const float a = fabsf(x);
+    if (!(a <= 3.402823466e+38f)) return 0;
+    const float q = __fadd_rn(__fdiv_rn(a, d), 0.5f);
+    const int m = q >= 2147483648.0f ? 2147483647 : (int)q;
+    return x < 0.0f ? -m : m;
 }
 
 // max |w| via integer atomicMax on the float bit pattern (non-negative floats order like ints)
@@ -50,10 +65,7 @@ __global__ void quantize_kernel(const float* __restrict__ w, int32_t* __restrict
     const long long n4 = n >> 2;
     const float4* w4 = reinterpret_cast<const float4*>(w);
     int4* l4 = reinterpret_cast<int4*>(lvl);
-    auto one = [&](float x) {
-        const int m = (int)__fadd_rn(__fdiv_rn(fabsf(x), d), 0.5f);
-        return x < 0.0f ? -m : m;
-    };
+    auto one = [&](float x) { return to_level(x, d); };
     const bool vec = ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(lvl)) & 15) == 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -121,9 +133,7 @@ __global__ void quantize_batch_kernel(const __grid_constant__ BatchDesc b, const
     const float d = stepsize(q, b.qp_density);
     if (blockIdx.x == 0 && threadIdx.x == 0 && qp_used) qp_used[t] = q;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float x = w[i];
-        const int m = (int)__fadd_rn(__fdiv_rn(fabsf(x), d), 0.5f);
-        const int l = x < 0.0f ? -m : m;
+        const int l = to_level(w[i], d);
         lvl[i] = l;
         if (rec) rec[i] = __fmul_rn((float)l, d);
     }

@@ -40,11 +40,13 @@ class LSAStep:
     lr             Adam learning rate (tune_model: torch.optim.Adam(tuning_params, lr=self.learning_rate))
     requantize     optional callable run at the start of every step (BASELINE cfg2 times quantise + render + update
                    together); None when the levels are frozen for the whole tuning run, as in tune_model
+    H, W, K        image size and intrinsics, only needed when the rays go through the NDC warp (dataset_type='llff' without
+                   no_ndc: render() then calls ndc_rays(H, W, K[0][0], 1., ...), run_nerf.py:131-133)
     render_kwargs  extra keyword arguments for render.create_nerf (perturb, white_bkgd, N_samples, ...)
     """
 
     def __init__(self, wrapper, n_rays: int, lr: float = 1e-4, requantize: Optional[Callable[[], None]] = None,
-                 near: float = 2.0, far: float = 6.0, chunk: int = 32768, **render_kwargs):
+                 near: float = 2.0, far: float = 6.0, chunk: int = 32768, H: int = 4, W: int = 4, K=None, **render_kwargs):
         self.wrapper = wrapper
         self.n_rays = int(n_rays)
         self.requantize = requantize
@@ -57,6 +59,10 @@ class LSAStep:
         # capturable: the step counters live on the device, so optimizer.step() can sit inside a CUDA graph
         self.optimizer = torch.optim.Adam(self.params, lr=lr, fused=True, capturable=True)
         self.train_kwargs, _ = R.create_nerf(wrapper, **render_kwargs)
+        self.H, self.W, self.K = int(H), int(W), K
+        if self.train_kwargs.get("ndc", True) and K is None:
+            raise ValueError("this configuration renders through the NDC warp (create_nerf omits ndc=False for dataset_type='llff'): "
+                             "pass H, W and the intrinsics K")
         self.rays = torch.zeros(2, self.n_rays, 3, device=dev)         # [rays_o, rays_d] as run_nerf.py:739 passes batch_rays
         self.target = torch.zeros(self.n_rays, 3, device=dev)
         self.graph = None
@@ -66,7 +72,7 @@ class LSAStep:
     def step(self, rays: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         if self.requantize is not None:
             self.requantize()
-        rgb, _, _, extras = R.render(4, 4, None, chunk=self.chunk, rays=(rays[0], rays[1]), near=self.near, far=self.far,
+        rgb, _, _, extras = R.render(self.H, self.W, self.K, chunk=self.chunk, rays=(rays[0], rays[1]), near=self.near, far=self.far,
                                      retraw=False, **self.train_kwargs)
         loss = R.img2mse(rgb, target) + R.img2mse(extras["rgb0"], target)
         loss.backward()

@@ -59,8 +59,9 @@ class NeRF(nn.Module):
             self.output_linear = nn.Linear(W, output_ch)
         self._packed: Optional[packed.PackedNet] = None
         self._packed_key = None
-        self.quant_levels = None       # optional: 12 int32 level tensors + 12 step sizes set by the quantiser
+        self.quant_levels = None       # optional: 12 int32 level tensors + 12 step sizes, see set_quant_levels
         self.quant_steps = None
+        self._quant_key = None         # identity + version of the float weights the levels belong to
 
     def forward(self, x):
         input_pts, input_views = torch.split(x, [self.input_ch, self.input_ch_views], dim=-1)
@@ -93,12 +94,26 @@ class NeRF(nn.Module):
         """The 12 LSA scale parameters in layer order (None entries when the model has no LSA)."""
         return [getattr(l, "weight_scaling", None) for l in self.layers()]
 
+    def _weight_key(self):
+        return tuple((l.weight.data_ptr(), l.weight._version) for l in self.layers())
+
+    def set_quant_levels(self, levels, steps):
+        """Attach the integer levels (12 int32 tensors [out,in]) and step sizes whose product the float `weight`
+        parameters hold right now.  They are the MLP kernels' operands for as long as the float weights stay untouched:
+        any later load_state_dict / in-place update of a weight (a version-counter bump) drops them, and the renderer
+        packs the float weights again -- so state_dict(), NeRF.forward and the fused path never disagree."""
+        self.quant_levels, self.quant_steps = (list(levels), list(steps)) if levels is not None else (None, None)
+        self._quant_key = self._weight_key() if levels is not None else None
+        self._packed = None
+
     def packed_net(self) -> packed.PackedNet:
         """Pack (or reuse) the frozen weights; biases and scales are refreshed by the caller."""
         if not self.supported():
             raise NotImplementedError("the fused kernels implement the vanilla NeRF architecture only "
                                       "(D=8, W=256, input_ch=63, input_ch_views=27, skips=[4], use_viewdirs=True)")
         ls = self.layers()
+        if self.quant_levels is not None and self._quant_key is not None and self._quant_key != self._weight_key():
+            self.quant_levels = self.quant_steps = self._quant_key = None       # the float weights moved on: levels are stale
         key = tuple((l.weight.data_ptr(), l.weight._version, l.bias.data_ptr(), l.bias._version) for l in ls) + \
             (id(self.quant_levels),)
         if self._packed is None or key != self._packed_key:
@@ -119,6 +134,8 @@ class NeRF(nn.Module):
                 new.__dict__[k] = None
             else:
                 new.__dict__[k] = copy.deepcopy(v, memo)
+        if new.__dict__.get("quant_levels") is not None:
+            new._quant_key = new._weight_key()          # the copy's weights are new tensors holding the same values
         return new
 
 

@@ -1,6 +1,7 @@
 """Device-resident packed form of one NeRF network (csrc/net_layout.h) and the raw kernel entry
 points that consume it.  PyTorch is used for device memory and the current stream only."""
 import ctypes
+import warnings
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -14,6 +15,17 @@ LAYER_IN = (63, 256, 256, 256, 256, 319, 256, 256, 256, 256, 283, 128)
 # flat per-channel order used by the kernels: pts0..7, feature, views, alpha, rgb
 CHANNEL_ORDER = tuple(range(8)) + (9, 10, 8, 11)
 NUM_CHANNELS = 2436
+
+
+# Integer levels are the tensor-core operands, exact in fp16 up to EXACT_LEVEL.  Beyond it nerfq_pack_net rounds a level to
+# 11 significant bits (relative error <= 2^-12, what any fp16 weight gets; csrc/pack.cu): "warn" reports that once per
+# packed network, "raise" refuses, "ignore" stays silent.
+EXACT_LEVEL = 2048
+LEVEL_RANGE_POLICY = "warn"
+
+
+class LevelRangeError(_lib.NerfqError):
+    pass
 
 
 def _stream() -> int:
@@ -60,8 +72,35 @@ class PackedNet:
         dl = (ctypes.c_float * 12)(*[float(d) for d in deltas])
         _lib.check(L.nerfq_pack_net(self.buf.data_ptr(), ptrs, dl, int(is_int), _stream()), "nerfq_pack_net")
         self._keep = ws
+        self.is_int = is_int
+        self._max_abs = torch.empty(12, dtype=torch.float32, device=dev)
+        _lib.check(L.nerfq_pack_status(self.buf.data_ptr(), self._max_abs.data_ptr(), _stream()), "nerfq_pack_status")
+        self._range_checked = False
+        if not torch.cuda.is_current_stream_capturing():
+            self.check_range()
         self.bias_flat = flatten_channels(biases).to(dev)
         self.set_scales(scales)
+
+    def max_abs_per_layer(self):
+        """max |level| (or |weight|) of the 12 layers as packed (synchronises)."""
+        return [float(v) for v in self._max_abs.cpu()]
+
+    def check_range(self):
+        """Applies LEVEL_RANGE_POLICY to the operand range found by nerfq_pack_net.  Non-finite weights always raise."""
+        self._range_checked = True
+        mx = self.max_abs_per_layer()
+        bad = [LAYER_NAMES[l] for l, v in enumerate(mx) if not (v <= 3.0e38)]
+        if bad:
+            raise LevelRangeError(f"non-finite weights in {bad}")
+        if not self.is_int or LEVEL_RANGE_POLICY == "ignore":
+            return
+        over = {LAYER_NAMES[l]: int(v) for l, v in enumerate(mx) if v > EXACT_LEVEL}
+        if over:
+            msg = (f"quantisation levels beyond +-{EXACT_LEVEL} are not exact fp16 tensor-core operands; they are rounded to 11 "
+                   f"significant bits (relative error <= 2^-12): max |level| {over}")
+            if LEVEL_RANGE_POLICY == "raise":
+                raise LevelRangeError(msg)
+            warnings.warn(msg, RuntimeWarning, stacklevel=3)
 
     def set_scales(self, scales: Optional[Sequence[torch.Tensor]] = None, flat: Optional[torch.Tensor] = None):
         """(Re)load the LSA scales: the epilogue constant becomes delta*scale per output channel."""
