@@ -197,7 +197,8 @@ def run_cuda(args):
     torch.manual_seed(0)
     wrapper = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params().to(dev)
     master = {k: v.detach().clone() for k, v in wrapper.state_dict().items()}      # unquantised float weights
-    R.DATA_PARALLEL["enabled"] = world > 1
+    from nerfq_b200 import distributed as D
+    D.enable_data_parallel(world > 1)
 
     o_h, d_h, t_h = synth_batch(RAYS_PER_GPU, 2 + 10 * rank)
     rays_h = torch.stack([o_h, d_h], 0).pin_memory()          # [2, N, 3] as run_nerf.py:739 passes `batch_rays`

@@ -100,6 +100,16 @@ unsigned long long nerfq_mlp_save_bytes(long long n_points);
 int nerfq_mlp_backward(void* packed, const float* d_raw, const float* raw, const void* save, long long n_points,
                        float* d_scale, int max_ctas, nerfq_stream_t stream);
 
+/* The same in two halves, for data-parallel tuning (the reference is single-GPU, README.md:76): `partial`
+ * accumulates s*ds into the caller's fixed-point buffer grad_fix (DEVICE int64[nerfq_mlp_grad_fix_bytes()/8], value *
+ * 2^48, zeroed by the caller once); the ranks then sum their buffers as INTEGERS (e.g. ncclInt64 / ncclSum) and `finalize`
+ * converts: d_scale[i] += grad_fix[i] / 2^48 / scale[i], leaving grad_fix zeroed.  Integer sums are order-independent, so
+ * N ranks x B rays give bit-identical gradients to one rank x N*B rays (given the same per-ray loss weights). */
+unsigned long long nerfq_mlp_grad_fix_bytes(void);
+int nerfq_mlp_backward_partial(const void* packed, const float* d_raw, const float* raw, const void* save, long long n_points,
+                               long long* grad_fix, int max_ctas, nerfq_stream_t stream);
+int nerfq_mlp_backward_finalize(const void* packed, long long* grad_fix, float* d_scale, nerfq_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Ray-side kernels
  * ---------------------------------------------------------------------------------------------- */
@@ -130,8 +140,10 @@ int nerfq_camera_rays(int H, int W, const float* K4, const float* c2w12, int ndc
 int nerfq_pack_rays(const float* rays_o, const float* rays_d, long long n, int ndc, int H, int W, float focal, float near,
                     float far, float* rays_out, nerfq_stream_t stream);
 
-/* img2mse (x2) and gradient, run_nerf_helpers.py:12 and run_nerf.py:741-751.  loss2[2] must be zeroed. */
-int nerfq_mse_grad(const float* rgb, const float* rgb0, const float* target, long long n_rays, float* d_rgb,
+/* img2mse (x2) and gradient, run_nerf_helpers.py:12 and run_nerf.py:741-751.  loss2[2] must be zeroed.
+ * n_norm: the number of rays the mean runs over (0 = n_rays); a data-parallel rank passes the GLOBAL batch size so that
+ * its loss terms and gradients are the rank's share of the global mean. */
+int nerfq_mse_grad(const float* rgb, const float* rgb0, const float* target, long long n_rays, long long n_norm, float* d_rgb,
                    float* d_rgb0, float* loss2, nerfq_stream_t stream);
 
 #ifdef __cplusplus

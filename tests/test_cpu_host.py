@@ -102,14 +102,19 @@ _WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
 import nerfq_b200
-from nerfq_b200.distributed import allreduce_scale_grads, shard_range
+from nerfq_b200.distributed import allreduce_fixed, shard_range
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["PORT"], rank=rank, world_size=world)
-g0 = torch.full((2436,), float(rank + 1)); g1 = torch.arange(2436, dtype=torch.float32) * (rank + 1)
-a, b = allreduce_scale_grads(g0, g1)
-assert torch.allclose(a, torch.full((2436,), 1.5)) and torch.allclose(b, torch.arange(2436, dtype=torch.float32) * 1.5)
-a, b = allreduce_scale_grads(g0, None)
-assert b is None and torch.allclose(a, torch.full((2436,), 1.5))
+# the data-parallel gradient exchange: every rank holds 64-bit fixed-point partial sums (value * 2^48) of ITS rays; the
+# integer all-reduce must equal the sum a single rank would have formed over all rays, bit for bit, for any split
+gen = torch.Generator().manual_seed(7)
+terms = (torch.randn(64, 2440, generator=gen, dtype=torch.float64) * 1e-4 * 2.0 ** 48).round().to(torch.int64)     # 64 "rays"
+whole = terms.sum(0)
+lo, cnt = shard_range(64, rank, world)
+mine = terms[lo:lo + cnt].sum(0)
+got = allreduce_fixed(mine.clone())
+assert torch.equal(got, whole)
+assert not torch.equal(mine, whole)
 # sharded "render": each rank fills its pixel slice, all_gather with padding reassembles the image
 n = 1001
 f, c = shard_range(n, rank, world)

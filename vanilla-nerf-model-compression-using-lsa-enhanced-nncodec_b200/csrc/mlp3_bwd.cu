@@ -350,16 +350,15 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-// d_scale[i] += tmp[i] / s[i];  tmp[i] = 0  (the scratch is left zeroed for the next launch).
+// d_scale[i] += fix[i] / 2^kGradFixShift / s[i];  fix[i] = 0  (the scratch is left zeroed for the next launch).
 // A scale of exactly 0 makes y - b = 0, so the kernel cannot recover sum dY (L x) delta from its saved activations:
 // that channel's gradient is reported as 0 (finite) instead of 0/0 -- documented in include/nerfq.h.
-__global__ void mlp3_backward_finalize_kernel(uint8_t* packed, float* __restrict__ d_scale) {
-    long long* tmp = reinterpret_cast<long long*>(packed + kOffGradTmp3);
+__global__ void mlp3_backward_finalize_kernel(const uint8_t* packed, long long* __restrict__ fix, float* __restrict__ d_scale) {
     const float* scale = reinterpret_cast<const float*>(packed + kOffScale);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < kNumChannels) {
-        const long long q = tmp[i];
-        tmp[i] = 0;
+        const long long q = fix[i];
+        fix[i] = 0;
         const float sc = scale[i];
         if (q != 0 && sc != 0.0f) d_scale[i] += (float)((double)q * (1.0 / (double)(1ull << kGradFixShift))) / sc;
     }
@@ -371,11 +370,14 @@ static unsigned long long* g_trace3b = nullptr;
 // Profiling aid (not part of include/nerfq.h): see nerfq_mlp_set_trace.
 extern "C" void nerfq_mlp_set_trace_bwd(unsigned long long* buf) { g_trace3b = buf; }
 
-extern "C" int nerfq_mlp_backward(void* packed, const float* d_raw, const float* raw, const void* save, long long n_points,
-                                   float* d_scale, int max_ctas, cudaStream_t stream) {
+extern "C" unsigned long long nerfq_mlp_grad_fix_bytes(void) { return nerfq::kGradTmp3Bytes; }
+
+// The backward kernel proper: accumulates s*ds per channel into `grad_fix` (64-bit fixed point, see mlp3_layout.h).
+extern "C" int nerfq_mlp_backward_partial(const void* packed, const float* d_raw, const float* raw, const void* save, long long n_points,
+                                           long long* grad_fix, int max_ctas, cudaStream_t stream) {
     using namespace nerfq;
     if (n_points == 0) return 0;
-    if (!packed || !d_raw || !raw || !save || !d_scale || n_points < 0) return -1;
+    if (!packed || !d_raw || !raw || !save || !grad_fix || n_points < 0) return -1;
     static const Prog3Bwd prog = make_prog3_bwd();
     const int n_groups = (int)((n_points + kGroupPts - 1) / kGroupPts);
     int dev = 0, sms = 0;
@@ -383,11 +385,7 @@ extern "C" int nerfq_mlp_backward(void* packed, const float* d_raw, const float*
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
     const int grid = n_groups < sms ? n_groups : sms;
-    // the kernel accumulates s*ds into a scratch array of the packed buffer (zeroed by nerfq_pack_net and by every
-    // finalize), the finalize kernel divides by the LSA scale and adds into d_scale
-    uint8_t* pk = (uint8_t*)packed;
-    Bwd3Params prm{(const uint8_t*)packed, d_raw, raw, (const uint8_t*)save, reinterpret_cast<long long*>(pk + kOffGradTmp3), n_points, n_groups,
-                   g_trace3b, prog};
+    Bwd3Params prm{(const uint8_t*)packed, d_raw, raw, (const uint8_t*)save, grad_fix, n_points, n_groups, g_trace3b, prog};
     if (g_trace3b) {
         if (cudaFuncSetAttribute(mlp3_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS3Bytes) != cudaSuccess) return -2;
         mlp3_backward_kernel<true><<<grid, kThreads3, kS3Bytes, stream>>>(prm);
@@ -395,6 +393,24 @@ extern "C" int nerfq_mlp_backward(void* packed, const float* d_raw, const float*
         if (cudaFuncSetAttribute(mlp3_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kS3Bytes) != cudaSuccess) return -2;
         mlp3_backward_kernel<false><<<grid, kThreads3, kS3Bytes, stream>>>(prm);
     }
-    mlp3_backward_finalize_kernel<<<(kNumChannels + 255) / 256, 256, 0, stream>>>(pk, d_scale);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+extern "C" int nerfq_mlp_backward_finalize(const void* packed, long long* grad_fix, float* d_scale, cudaStream_t stream) {
+    using namespace nerfq;
+    if (!packed || !grad_fix || !d_scale) return -1;
+    mlp3_backward_finalize_kernel<<<(kNumChannels + 255) / 256, 256, 0, stream>>>((const uint8_t*)packed, grad_fix, d_scale);
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+// partial + finalize through the scratch array inside the packed buffer (zeroed by nerfq_pack_net and by every finalize)
+extern "C" int nerfq_mlp_backward(void* packed, const float* d_raw, const float* raw, const void* save, long long n_points,
+                                   float* d_scale, int max_ctas, cudaStream_t stream) {
+    using namespace nerfq;
+    if (n_points == 0) return 0;
+    if (!packed || !d_scale) return -1;
+    long long* fix = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(packed) + kOffGradTmp3);
+    const int rc = nerfq_mlp_backward_partial(packed, d_raw, raw, save, n_points, fix, max_ctas, stream);
+    if (rc != 0) return rc;
+    return nerfq_mlp_backward_finalize(packed, fix, d_scale, stream);
 }

@@ -397,9 +397,10 @@ __global__ void pack_rays_kernel(const CamParams cp, const float* __restrict__ r
 // LSA objective: loss = mean((rgb-t)^2) + mean((rgb0-t)^2); gradients 2(rgb-t)/(3N)
 // ---------------------------------------------------------------------------------------------
 __global__ void mse_grad_kernel(const float* __restrict__ rgb, const float* __restrict__ rgb0, const float* __restrict__ target,
-                                long long n3, float* __restrict__ d_rgb, float* __restrict__ d_rgb0, float* __restrict__ loss2) {
+                                long long n3, long long n3_norm, float* __restrict__ d_rgb, float* __restrict__ d_rgb0,
+                                float* __restrict__ loss2) {
     float s0 = 0.f, s1 = 0.f;
-    const float k = 2.0f / (float)n3;
+    const float k = 2.0f / (float)n3_norm;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long long)gridDim.x * blockDim.x) {
         const float t = target[i];
         const float a = rgb[i] - t;
@@ -413,8 +414,8 @@ __global__ void mse_grad_kernel(const float* __restrict__ rgb, const float* __re
     }
     s0 = warp_sum(s0); s1 = warp_sum(s1);
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(loss2 + 0, s0 / (float)n3);
-        atomicAdd(loss2 + 1, s1 / (float)n3);
+        atomicAdd(loss2 + 0, s0 / (float)n3_norm);
+        atomicAdd(loss2 + 1, s1 / (float)n3_norm);
     }
 }
 
@@ -504,13 +505,14 @@ extern "C" int nerfq_pack_rays(const float* rays_o, const float* rays_d, long lo
 }
 
 // loss2 must be zeroed by the caller; receives {mse(rgb,t), mse(rgb0,t)}.
-extern "C" int nerfq_mse_grad(const float* rgb, const float* rgb0, const float* target, long long n_rays, float* d_rgb,
+extern "C" int nerfq_mse_grad(const float* rgb, const float* rgb0, const float* target, long long n_rays, long long n_norm, float* d_rgb,
                               float* d_rgb0, float* loss2, cudaStream_t stream) {
     if (n_rays == 0) return 0;
-    if (!rgb || !target || !d_rgb || !loss2 || (rgb0 && !d_rgb0) || n_rays < 0) return -1;
+    if (!rgb || !target || !d_rgb || !loss2 || (rgb0 && !d_rgb0) || n_rays < 0 || n_norm < 0) return -1;
     const long long n3 = n_rays * 3;
+    const long long n3_norm = (n_norm > 0 ? n_norm : n_rays) * 3;
     long long blocks = (n3 + 255) / 256;
     if (blocks > 592) blocks = 592;
-    mse_grad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rgb, rgb0, target, n3, d_rgb, d_rgb0, loss2);
+    mse_grad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rgb, rgb0, target, n3, n3_norm, d_rgb, d_rgb0, loss2);
     return launch_ok();
 }

@@ -1,6 +1,6 @@
 """Multi-GPU plumbing (one process per GPU, torch.distributed over NCCL): rays are independent units, so
 test-view rendering shards the pixel range with no data-path collective, and data-parallel LSA tuning needs
-one all-reduce of the 4,872 scale gradients (19.5 KB) per step.  The reference itself is single-GPU
+one all-reduce of the scale gradients per network and step (2 x 19.5 KB of 64-bit fixed-point sums).  The reference itself is single-GPU
 (README.md:76); SURVEY section 8(e) defines this sharding."""
 from typing import Optional, Tuple
 
@@ -15,16 +15,23 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     return first, base + (1 if rank < rem else 0)
 
 
-def allreduce_scale_grads(g0: torch.Tensor, g1: Optional[torch.Tensor], group=None):
-    """Mean of the flat LSA-scale gradients over the ranks, as one collective."""
-    world = dist.get_world_size(group)
-    if world == 1:
-        return g0, g1
-    buf = torch.cat([g0, g1]) if g1 is not None else g0.clone()
-    dist.all_reduce(buf, group=group)
-    buf /= world
-    n = g0.numel()
-    return buf[:n], (buf[n:] if g1 is not None else None)
+def allreduce_fixed(fix: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum the ranks' fixed-point scale-gradient buffers (int64, value * 2^48; nerfq_mlp_backward_partial) in place.
+    Integer addition is associative, so the sum -- and the float gradient nerfq_mlp_backward_finalize derives from it --
+    does not depend on the number of ranks or on NCCL's reduction order: N ranks x B rays == 1 rank x N*B rays, bit for
+    bit, when every rank weights its rays by 1 / (global batch)."""
+    assert fix.dtype == torch.int64
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(fix, op=dist.ReduceOp.SUM, group=group)
+    return fix
+
+
+def enable_data_parallel(enabled: bool = True, group=None):
+    """Switch the renderer's backward (render._backward_pipeline, used by autograd and by lsa.LSAStep) to data parallel."""
+    from . import render
+    render.DATA_PARALLEL["enabled"] = bool(enabled) and dist.is_initialized() and dist.get_world_size(group) > 1
+    render.DATA_PARALLEL["group"] = group
+    return render.DATA_PARALLEL["enabled"]
 
 
 def render_view_sharded(H: int, W: int, K, c2w, render_kwargs: dict, chunk: int = 32768, ndc: bool = False, near: float = 2.0,

@@ -16,7 +16,7 @@ from typing import Callable, Optional
 
 import torch
 
-from . import codec
+from . import codec, ops, packed
 from . import render as R
 
 
@@ -43,7 +43,16 @@ class LSAStep:
     H, W, K        image size and intrinsics, only needed when the rays go through the NDC warp (dataset_type='llff' without
                    no_ndc: render() then calls ndc_rays(H, W, K[0][0], 1., ...), run_nerf.py:131-133)
     render_kwargs  extra keyword arguments for render.create_nerf (perturb, white_bkgd, N_samples, ...)
-    """
+
+    The 24 `weight_scaling` parameters are re-pointed at slices of ONE flat [2, 2436] tensor in the kernels' channel
+    order (their values, names and state_dict entries are unchanged), so a step needs no gather of scales or scatter of
+    gradients: the kernels read and write the flat buffers, Adam updates one tensor, and every parameter's `.grad` is a
+    view of the flat gradient.  Launches per step: pack_rays, 2 x (set_scale_bias, MLP forward, composite), coarse depths,
+    sample+merge, mse_grad, 2 x (composite backward, MLP backward, finalize), fused Adam, 2 memsets, the loss sum and the
+    RNG draws of `perturb`.
+
+    Data parallel (distributed.enable_data_parallel): the objective is the mean over the GLOBAL batch (world x n_rays);
+    each rank's returned loss is its share of it (the sum over ranks is the global loss)."""
 
     def __init__(self, wrapper, n_rays: int, lr: float = 1e-4, requantize: Optional[Callable[[], None]] = None,
                  near: float = 2.0, far: float = 6.0, chunk: int = 32768, H: int = 4, W: int = 4, K=None, **render_kwargs):
@@ -56,33 +65,83 @@ class LSAStep:
         if dev.type != "cuda":
             raise RuntimeError("LSAStep needs the model on a CUDA device (there is no CPU path)")
         self.device = dev
-        # capturable: the step counters live on the device, so optimizer.step() can sit inside a CUDA graph
-        self.optimizer = torch.optim.Adam(self.params, lr=lr, fused=True, capturable=True)
         self.train_kwargs, _ = R.create_nerf(wrapper, **render_kwargs)
         self.H, self.W, self.K = int(H), int(W), K
-        if self.train_kwargs.get("ndc", True) and K is None:
+        self.ndc = bool(self.train_kwargs.get("ndc", True))
+        if self.ndc and K is None:
             raise ValueError("this configuration renders through the NDC warp (create_nerf omits ndc=False for dataset_type='llff'): "
                              "pass H, W and the intrinsics K")
+        self.flat = self._flatten_scales()
+        self.flat_param = torch.nn.Parameter(self.flat)
+        self.grad = torch.zeros_like(self.flat)
+        self.flat_param.grad = self.grad
+        for net_i, net in enumerate((wrapper.model, wrapper.model_fine)):
+            for l, p, lo, n in self._slices(net):
+                p.grad = self.grad[net_i, lo:lo + n].view(n, 1)
+        # capturable: the step counter lives on the device, so optimizer.step() can sit inside a CUDA graph
+        self.optimizer = torch.optim.Adam([self.flat_param], lr=lr, fused=True, capturable=True)
+        self.loss2 = torch.zeros(2, device=dev)
         self.rays = torch.zeros(2, self.n_rays, 3, device=dev)         # [rays_o, rays_d] as run_nerf.py:739 passes batch_rays
         self.target = torch.zeros(self.n_rays, 3, device=dev)
         self.graph = None
         self.loss = None
 
+    @staticmethod
+    def _slices(net):
+        """(layer index, weight_scaling parameter, first channel, channels) in the kernels' flat channel order."""
+        out, lo = [], 0
+        scales = net.scale_tensors()
+        for l in packed.CHANNEL_ORDER:
+            n = packed.LAYER_OUT[l]
+            out.append((l, scales[l], lo, n))
+            lo += n
+        return out
+
+    def _flatten_scales(self) -> torch.Tensor:
+        flat = torch.empty((2, packed.NUM_CHANNELS), dtype=torch.float32, device=self.device)
+        with torch.no_grad():
+            for net_i, net in enumerate((self.wrapper.model, self.wrapper.model_fine)):
+                for l, p, lo, n in self._slices(net):
+                    if p is None:
+                        raise ValueError("LSAStep needs a model with LSA parameters (model.LSA(w).add_lsa_params())")
+                    flat[net_i, lo:lo + n].copy_(p.detach().reshape(-1))
+                    p.data = flat[net_i, lo:lo + n].view(n, 1)
+        return flat
+
+    def world(self) -> int:
+        import torch.distributed as dist
+        if R.DATA_PARALLEL["enabled"] and dist.is_initialized():
+            return dist.get_world_size(R.DATA_PARALLEL.get("group"))
+        return 1
+
     # the iteration body, eager
     def step(self, rays: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         if self.requantize is not None:
             self.requantize()
-        rgb, _, _, extras = R.render(self.H, self.W, self.K, chunk=self.chunk, rays=(rays[0], rays[1]), near=self.near, far=self.far,
-                                     retraw=False, **self.train_kwargs)
-        loss = R.img2mse(rgb, target) + R.img2mse(extras["rgb0"], target)
-        loss.backward()
-        self.optimizer.step()
-        return loss.detach()
+        kw = self.train_kwargs
+        focal = float(self.K[0][0]) if self.ndc else 1.0
+        packed_rays = ops.pack_rays(rays[0], rays[1], self.ndc, self.H, self.W, focal, self.near, self.far)
+        n_norm = self.n_rays * self.world()
+        self.loss2.zero_()
+        self.grad.zero_()
+        with torch.no_grad():
+            for i in range(0, self.n_rays, self.chunk):
+                cfg = R._make_cfg(packed_rays[i:i + self.chunk], kw["network_fn"], kw["network_fine"], kw["N_samples"], kw["N_importance"],
+                                  kw.get("lindisp", False), kw["perturb"], kw["white_bkgd"], kw["raw_noise_std"], False)
+                outs, st = R._forward_pipeline(cfg, self.flat[0], self.flat[1], save=True)
+                rgb, rgb0 = (outs[0], outs[3]) if cfg.Ni > 0 else (outs[0], None)
+                _, d_rgb, d_rgb0 = ops.mse_grad(rgb, rgb0, target[i:i + self.chunk], n_norm=n_norm, loss2=self.loss2)
+                if cfg.Ni > 0:
+                    R._backward_pipeline(cfg, st, d_rgb, d_rgb0, g_out=self.grad)
+                else:
+                    R._backward_pipeline(cfg, st, None, d_rgb, g_out=self.grad)
+            self.optimizer.step()
+            return self.loss2.sum()
 
     def _init_optimizer_state(self):
-        """Create Adam's per-parameter state (step, exp_avg, exp_avg_sq) the way torch.optim.Adam does on its first
-        step().  Inside a capture that lazy initialisation would be RECORDED, and every replay would start from a fresh
-        optimizer; with the state created beforehand the graph only holds the update itself."""
+        """Create Adam's state (step, exp_avg, exp_avg_sq) the way torch.optim.Adam does on its first step().  Inside a
+        capture that lazy initialisation would be RECORDED, and every replay would start from a fresh optimizer; with the
+        state created beforehand the graph only holds the update itself."""
         for group in self.optimizer.param_groups:
             for p in group["params"]:
                 st = self.optimizer.state[p]
@@ -95,26 +154,16 @@ class LSAStep:
         """Record the iteration in a CUDA graph (after `warmup` eager iterations on a side stream, which also update
         the parameters; 0 is allowed).  Raises if anything on the path is not capturable; the eager `step` stays usable."""
         self._init_optimizer_state()
+        R._DPState.get(self.device)                       # data-parallel scratch exists before the capture
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self.optimizer.zero_grad(set_to_none=True)
                 self.step(self.rays, self.target)
         torch.cuda.current_stream(self.device).wait_stream(side)
-        self.optimizer.zero_grad(set_to_none=True)        # backward() then allocates .grad inside the graph's pool
         graph = torch.cuda.CUDAGraph()
-        # The parameters' AccumulateGrad nodes were created on whatever stream first ran a backward; the capture stream
-        # differs from it by construction, which autograd reports once per process.  The capture orders the streams itself.
-        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
-        if quiet is not None:
-            quiet(False)
-        try:
-            with torch.cuda.graph(graph):
-                self.loss = self.step(self.rays, self.target)
-        finally:
-            if quiet is not None:
-                quiet(True)
+        with torch.cuda.graph(graph):
+            self.loss = self.step(self.rays, self.target)
         self.graph = graph
         return self
 
@@ -122,7 +171,6 @@ class LSAStep:
         """rays [2, n_rays, 3] and target [n_rays, 3], on the host (pinned for an asynchronous copy) or on the device.
         Returns the loss as a device scalar; it is overwritten by the next call."""
         if self.graph is None:
-            self.optimizer.zero_grad(set_to_none=True)
             return self.step(rays.to(self.device, non_blocking=True), target.to(self.device, non_blocking=True))
         self.rays.copy_(rays, non_blocking=True)
         self.target.copy_(target, non_blocking=True)

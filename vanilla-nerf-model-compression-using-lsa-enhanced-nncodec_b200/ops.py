@@ -36,8 +36,11 @@ _PROTOS = {
                                      _c.c_float, _c.c_longlong, _c.c_longlong, _c.c_void_p, _c.c_void_p]),
     "nerfq_pack_rays": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_float,
                                    _c.c_float, _c.c_void_p, _c.c_void_p]),
-    "nerfq_mse_grad": (_c.c_int, [_c.c_void_p] * 3 + [_c.c_longlong] + [_c.c_void_p] * 4),
+    "nerfq_mse_grad": (_c.c_int, [_c.c_void_p] * 3 + [_c.c_longlong, _c.c_longlong] + [_c.c_void_p] * 4),
     "nerfq_mlp_backward": (_c.c_int, [_c.c_void_p] * 4 + [_c.c_longlong, _c.c_void_p, _c.c_int, _c.c_void_p]),
+    "nerfq_mlp_backward_partial": (_c.c_int, [_c.c_void_p] * 4 + [_c.c_longlong, _c.c_void_p, _c.c_int, _c.c_void_p]),
+    "nerfq_mlp_backward_finalize": (_c.c_int, [_c.c_void_p] * 4),
+    "nerfq_mlp_grad_fix_bytes": (_c.c_ulonglong, []),
 }
 _bound = False
 
@@ -191,8 +194,10 @@ def pack_rays(rays_o: torch.Tensor, rays_d: torch.Tensor, ndc: bool, H: int, W: 
     return out
 
 
-def mse_grad(rgb: torch.Tensor, rgb0: Optional[torch.Tensor], target: torch.Tensor):
-    """(loss2 = [mse(rgb,t), mse(rgb0,t)], d_rgb, d_rgb0) for loss = mse(rgb,t) + mse(rgb0,t)."""
+def mse_grad(rgb: torch.Tensor, rgb0: Optional[torch.Tensor], target: torch.Tensor, n_norm: int = 0,
+             loss2: Optional[torch.Tensor] = None):
+    """(loss2 = [mse(rgb,t), mse(rgb0,t)], d_rgb, d_rgb0) for loss = mse(rgb,t) + mse(rgb0,t).  n_norm: rays the mean runs
+    over (0 = this batch; a data-parallel rank passes the global batch size).  loss2: optional zeroed [2] output."""
     n = rgb.shape[0]
     rgb, target = _f32(rgb, n, 3), _f32(target, n, 3)
     d_rgb = torch.empty_like(rgb)
@@ -200,9 +205,10 @@ def mse_grad(rgb: torch.Tensor, rgb0: Optional[torch.Tensor], target: torch.Tens
     if rgb0 is not None:
         rgb0 = _f32(rgb0, n, 3)
         d_rgb0 = torch.empty_like(rgb0)
-    loss2 = torch.zeros(2, dtype=torch.float32, device=rgb.device)
-    _lib.check(L().nerfq_mse_grad(rgb.data_ptr(), _p(rgb0), target.data_ptr(), n, d_rgb.data_ptr(), _p(d_rgb0), loss2.data_ptr(), _stream()),
-               "nerfq_mse_grad")
+    if loss2 is None:
+        loss2 = torch.zeros(2, dtype=torch.float32, device=rgb.device)
+    _lib.check(L().nerfq_mse_grad(rgb.data_ptr(), _p(rgb0), target.data_ptr(), n, int(n_norm), d_rgb.data_ptr(), _p(d_rgb0),
+                                  loss2.data_ptr(), _stream()), "nerfq_mse_grad")
     return loss2, d_rgb, d_rgb0
 
 
@@ -215,4 +221,27 @@ def mlp_backward(net: PackedNet, d_raw: torch.Tensor, raw: torch.Tensor, save: t
         d_scale = torch.zeros(2436, dtype=torch.float32, device=raw.device)
     _lib.check(L().nerfq_mlp_backward(net.ptr, d_raw.data_ptr(), raw.data_ptr(), save.data_ptr(), n_points, d_scale.data_ptr(), max_ctas,
                                       _stream()), "nerfq_mlp_backward")
+    return d_scale
+
+
+def grad_fix_elems() -> int:
+    """int64 elements of one network's fixed-point scale-gradient buffer."""
+    return int(L().nerfq_mlp_grad_fix_bytes()) // 8
+
+
+def mlp_backward_partial(net: PackedNet, d_raw: torch.Tensor, raw: torch.Tensor, save: torch.Tensor, grad_fix: torch.Tensor,
+                         max_ctas: int = 0) -> torch.Tensor:
+    """The backward kernel alone: accumulates s*ds per channel into grad_fix (int64 [grad_fix_elems()], value * 2^48)."""
+    n_points = raw.shape[0] * raw.shape[1]
+    d_raw, raw = _f32(d_raw, *raw.shape), _f32(raw)
+    assert grad_fix.is_cuda and grad_fix.dtype == torch.int64 and grad_fix.is_contiguous() and grad_fix.numel() >= grad_fix_elems()
+    _lib.check(L().nerfq_mlp_backward_partial(net.ptr, d_raw.data_ptr(), raw.data_ptr(), save.data_ptr(), n_points, grad_fix.data_ptr(),
+                                              max_ctas, _stream()), "nerfq_mlp_backward_partial")
+    return grad_fix
+
+
+def mlp_backward_finalize(net: PackedNet, grad_fix: torch.Tensor, d_scale: torch.Tensor) -> torch.Tensor:
+    """d_scale[2436] += grad_fix / 2^48 / scale; grad_fix is left zeroed."""
+    assert d_scale.is_cuda and d_scale.dtype == torch.float32 and d_scale.is_contiguous() and d_scale.numel() == 2436
+    _lib.check(L().nerfq_mlp_backward_finalize(net.ptr, grad_fix.data_ptr(), d_scale.data_ptr(), _stream()), "nerfq_mlp_backward_finalize")
     return d_scale

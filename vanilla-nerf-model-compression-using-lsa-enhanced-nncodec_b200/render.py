@@ -29,7 +29,8 @@ mse2psnr = lambda x: -10. * torch.log(x) / torch.log(torch.tensor([10.], device=
 to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)
 
 TUNING = {"max_ctas": 0}      # kernel scheduling knob (bench/profiling)
-DATA_PARALLEL = {"enabled": False}              # all-reduce (mean) the LSA-scale gradients over torch.distributed
+# data-parallel LSA tuning: all-reduce the scale gradients over torch.distributed (group None = the default group)
+DATA_PARALLEL = {"enabled": False, "group": None}
 
 
 class _FusedQuery:
@@ -141,6 +142,80 @@ def _forward_pipeline(cfg: _Cfg, sc0, sc1, save: bool):
     return outs, st
 
 
+class _DPState:
+    """Per-device scratch of the data-parallel backward: the two networks' fixed-point gradient buffers (kept zeroed by
+    nerfq_mlp_backward_finalize) and the side stream the fine network's all-reduce runs on."""
+    _by_device = {}
+
+    def __init__(self, dev):
+        self.fix = torch.zeros((2, ops.grad_fix_elems()), dtype=torch.int64, device=dev)
+        self.side = torch.cuda.Stream(device=dev)
+
+    @classmethod
+    def get(cls, dev):
+        key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+        if key not in cls._by_device:
+            cls._by_device[key] = cls(dev)
+        return cls._by_device[key]
+
+
+def _backward_pipeline(cfg: _Cfg, st: dict, d_rgb1, d_rgb0, g_out: Optional[torch.Tensor] = None):
+    """d loss / d LSA scales of both networks from d loss / d rgb_map (fine, d_rgb1) and d loss / d rgb0 (coarse, d_rgb0):
+    compositing backward + MLP backward per network, fine first.  Returns (g0, g1): flat [2436] gradients in kernel channel
+    order for network_fn and network_fine (g1 None when the fine pass used network_fn).  g_out: optional zeroed [2, 2436]
+    buffer to accumulate into.
+
+    Data parallel (DATA_PARALLEL['enabled'], one process per GPU): every rank's kernels leave s*ds as 64-bit FIXED-POINT
+    sums; those are all-reduced as integers (NCCL int64 sum, 19.5 KB per network) before the conversion to float, so the
+    result does not depend on how the batch is split over ranks.  The fine network's all-reduce runs on a side stream under
+    the coarse network's backward kernels; only the coarse network's is exposed."""
+    mc = TUNING["max_ctas"]
+    rays = cfg.rays
+    dev = rays.device
+    dp = DATA_PARALLEL["enabled"]
+    own_fine = cfg.Ni > 0 and cfg.net1 is not None
+    if g_out is None:
+        g_out = torch.zeros((2, 2436), dtype=torch.float32, device=dev)
+    g0, g1 = g_out[0], (g_out[1] if own_fine else None)
+    passes = []                                   # (packed net, raw, z, save, noise, d_rgb, slot) in execution order
+    if cfg.Ni > 0 and d_rgb1 is not None:
+        passes.append((st["pn1"], st["raw1"], st["z1"], st["save1"], cfg.noise1, d_rgb1, 1 if own_fine else 0))
+    if d_rgb0 is not None:
+        passes.append((st["pn0"], st["raw0"], st["z0"], st["save0"], cfg.noise0, d_rgb0, 0))
+    if not dp:
+        for pn, raw, z, save, noise, d_rgb, slot in passes:
+            d_raw = ops.composite_bwd(raw, z, rays, cfg.white, d_rgb.contiguous(), noise)
+            ops.mlp_backward(pn, d_raw, raw, save, g_out[slot], max_ctas=mc)
+        return g0, g1
+    import torch.distributed as dist
+    group = DATA_PARALLEL.get("group")
+    dps = _DPState.get(dev)
+    main = torch.cuda.current_stream(dev)
+    pending = []                                  # slots whose all-reduce is in flight on the side stream
+    for i, (pn, raw, z, save, noise, d_rgb, slot) in enumerate(passes):
+        d_raw = ops.composite_bwd(raw, z, rays, cfg.white, d_rgb.contiguous(), noise)
+        ops.mlp_backward_partial(pn, d_raw, raw, save, dps.fix[slot], max_ctas=mc)
+        last = i + 1 == len(passes)
+        shared = not last and passes[i + 1][6] == slot          # the next pass accumulates into the same buffer
+        if shared:
+            continue
+        if last:
+            dist.all_reduce(dps.fix[slot], op=dist.ReduceOp.SUM, group=group)
+        else:
+            dps.side.wait_stream(main)
+            with torch.cuda.stream(dps.side):
+                dist.all_reduce(dps.fix[slot], op=dist.ReduceOp.SUM, group=group)
+            pending.append(slot)
+    if pending:
+        main.wait_stream(dps.side)
+    done = set()
+    for pn, _, _, _, _, _, slot in passes:
+        if slot not in done:
+            ops.mlp_backward_finalize(pn, dps.fix[slot], g_out[slot])
+            done.add(slot)
+    return g0, g1
+
+
 class _RenderRaysFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg: _Cfg, sc0, sc1):
@@ -153,43 +228,22 @@ class _RenderRaysFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         cfg, st = ctx.cfg, ctx.st
-        mc = TUNING["max_ctas"]
-        rays = cfg.rays
-        g0 = g1 = None
-        if cfg.Ni > 0:
-            d_rgb1, d_rgb0 = grads[0], grads[3]
-            own_fine = cfg.net1 is not None
-            acc = torch.zeros(2436, dtype=torch.float32, device=rays.device)
-            if d_rgb1 is not None:
-                d_raw1 = ops.composite_bwd(st["raw1"], st["z1"], rays, cfg.white, d_rgb1.contiguous(), cfg.noise1)
-                ops.mlp_backward(st["pn1"], d_raw1, st["raw1"], st["save1"], acc, max_ctas=mc)
-            if own_fine:
-                g1 = acc
-                acc = torch.zeros(2436, dtype=torch.float32, device=rays.device)
-            if d_rgb0 is not None:
-                d_raw0 = ops.composite_bwd(st["raw0"], st["z0"], rays, cfg.white, d_rgb0.contiguous(), cfg.noise0)
-                ops.mlp_backward(st["pn0"], d_raw0, st["raw0"], st["save0"], acc, max_ctas=mc)
-            g0 = acc
-        else:
-            d_rgb0 = grads[0]
-            g0 = torch.zeros(2436, dtype=torch.float32, device=rays.device)
-            if d_rgb0 is not None:
-                d_raw0 = ops.composite_bwd(st["raw0"], st["z0"], rays, cfg.white, d_rgb0.contiguous(), cfg.noise0)
-                ops.mlp_backward(st["pn0"], d_raw0, st["raw0"], st["save0"], g0, max_ctas=mc)
+        d_rgb1, d_rgb0 = (grads[0], grads[3]) if cfg.Ni > 0 else (None, grads[0])
+        if DATA_PARALLEL["enabled"]:
+            # the caller's loss is a mean over THIS rank's rays; the objective is the mean over the global batch
+            import torch.distributed as dist
+            inv = 1.0 / dist.get_world_size(DATA_PARALLEL.get("group"))
+            d_rgb1 = d_rgb1 * inv if d_rgb1 is not None else None
+            d_rgb0 = d_rgb0 * inv if d_rgb0 is not None else None
+        g0, g1 = _backward_pipeline(cfg, st, d_rgb1, d_rgb0)
         ctx.st = None
-        if DATA_PARALLEL["enabled"]:   # one 19.5 KB all-reduce per step; the loss is a mean over the GLOBAL batch
-            from .distributed import allreduce_scale_grads
-            g0, g1 = allreduce_scale_grads(g0, g1)
         return None, g0, (g1 if ctx.has1 else None)
 
 
-def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, retraw=False, lindisp=False, perturb=0.,
-                N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., pytest=False, verbose=False):
-    """run_nerf.py:348-457.  ray_batch rows: [o, d, near, far, viewdirs]; returns the same dict."""
-    assert ray_batch.is_cuda, "render_rays needs CUDA tensors (there is no CPU path)"
-    if ray_batch.shape[-1] <= 8:
-        raise NotImplementedError("the fused kernels implement the use_viewdirs=True configuration of the reference")
-    rays = ray_batch.float().contiguous()
+def _make_cfg(rays, network_fn, network_fine, N_samples, N_importance, lindisp, perturb, white_bkgd, raw_noise_std, pytest,
+              retraw=False) -> _Cfg:
+    """The per-call configuration of render_rays incl. the random draws the reference makes (run_nerf.py:395-403 t_rand,
+    run_nerf_helpers.py:131-145 u, run_nerf.py:316-322 noise), in the reference's order."""
     n, dev = rays.shape[0], rays.device
     cfg = _Cfg()
     cfg.net0, cfg.net1, cfg.rays = network_fn, network_fine, rays
@@ -216,6 +270,17 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, retr
             if pytest:
                 np.random.seed(0)
                 cfg.noise1 = torch.tensor(np.random.rand(n, cfg.S + cfg.Ni) * raw_noise_std, dtype=torch.float32, device=dev)
+    return cfg
+
+
+def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, retraw=False, lindisp=False, perturb=0.,
+                N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., pytest=False, verbose=False):
+    """run_nerf.py:348-457.  ray_batch rows: [o, d, near, far, viewdirs]; returns the same dict."""
+    assert ray_batch.is_cuda, "render_rays needs CUDA tensors (there is no CPU path)"
+    if ray_batch.shape[-1] <= 8:
+        raise NotImplementedError("the fused kernels implement the use_viewdirs=True configuration of the reference")
+    rays = ray_batch.float().contiguous()
+    cfg = _make_cfg(rays, network_fn, network_fine, N_samples, N_importance, lindisp, perturb, white_bkgd, raw_noise_std, pytest, retraw)
 
     sc0 = _scale_flat(network_fn)
     sc1 = _scale_flat(network_fine) if (network_fine is not None and cfg.Ni > 0) else None
