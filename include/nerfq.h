@@ -140,11 +140,15 @@ int nerfq_camera_rays(int H, int W, const float* K4, const float* c2w12, int ndc
 int nerfq_pack_rays(const float* rays_o, const float* rays_d, long long n, int ndc, int H, int W, float focal, float near,
                     float far, float* rays_out, nerfq_stream_t stream);
 
-/* img2mse (x2) and gradient, run_nerf_helpers.py:12 and run_nerf.py:741-751.  loss2[2] must be zeroed.
+/* img2mse (x2) and gradient, run_nerf_helpers.py:12 and run_nerf.py:741-751.  The two means are ADDED to loss2[2] (the
+ * caller zeroes it; several calls accumulate a chunked batch) by one thread in a fixed order: bit-reproducible.
  * n_norm: the number of rays the mean runs over (0 = n_rays); a data-parallel rank passes the GLOBAL batch size so that
- * its loss terms and gradients are the rank's share of the global mean. */
+ * its loss terms and gradients are the rank's share of the global mean.
+ * workspace: nerfq_mse_grad_workspace_bytes() bytes, zeroed once by the caller (the kernel leaves it re-armed); must not
+ * be shared by launches that may run concurrently. */
+unsigned long long nerfq_mse_grad_workspace_bytes(void);
 int nerfq_mse_grad(const float* rgb, const float* rgb0, const float* target, long long n_rays, long long n_norm, float* d_rgb,
-                   float* d_rgb0, float* loss2, nerfq_stream_t stream);
+                   float* d_rgb0, float* loss2, void* workspace, nerfq_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -158,11 +158,14 @@ def test_lsa_parameter_selection_matches_tune_model():
 
 
 def test_deepcabac_front_end_contract():
-    """nerfq_b200.deepcabac keeps the names baseline.py:24-57,89-98 binds; what is not on the GPU path refuses loudly
-    (no silent CPU fallback); argument errors are raised before any device work; empty tensors are accepted."""
+    """nerfq_b200.deepcabac keeps the names baseline.py:24-57,89-98 and coder/baseline.py:5-57 bind.  Elementwise
+    (de)quantisation belongs to the GPU kernels: without a CUDA device it refuses loudly (no silent CPU fallback) unless the
+    caller explicitly selects the host library; argument errors are raised before any device work; empty tensors are
+    accepted."""
     import numpy as np
     import pytest
     from nerfq_b200 import deepcabac
+    assert deepcabac.DEVICE == "cuda"
     enc, dec = deepcabac.Encoder(), deepcabac.Decoder()
     for name in ("initCtxModels", "quantLayer", "iae_v", "encodeLayer", "finish"):
         assert callable(getattr(enc, name))
@@ -171,12 +174,13 @@ def test_deepcabac_front_end_contract():
     enc.initCtxModels(10, 0)
     w = np.ones((4, 3), dtype=np.float32)
     out = np.zeros((4, 3), dtype=np.int32)
-    with pytest.raises(NotImplementedError):
-        enc.quantLayer(w, out, 1, 2, -20, 0.0, 10, 0)              # dependent quantisation stays on the host coder
-    with pytest.raises(NotImplementedError):
-        enc.encodeLayer(out, 0, 0)
-    with pytest.raises(NotImplementedError):
-        dec.decodeLayer(out, 0, 0)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            enc.quantLayer(w, out, 0, 2, -20, 0.0, 10, 0)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            dec.dequantLayer(w, out, 2, -20, 0)
+    assert enc.quantLayer(w, out, 1, 2, -20, 0.0, 10, 0) == -20        # dependent quantisation: host trellis search by design
+    assert np.abs(out * 0.03125 - w).max() <= 2 * 0.03125
     with pytest.raises(TypeError):
         enc.quantLayer(w.astype(np.float64), out, 0, 2, -20, 0.0, 10, 0)
     with pytest.raises(ValueError):

@@ -152,7 +152,7 @@ def test_llff_configuration_ni64_ndc_and_lindisp(dev):
 def test_every_qp_of_the_sweep_bit_exact(dev):
     """BASELINE cfg5: for EVERY qp in -38..-10 the levels of every tensor of the wrapper (24 weights at qp, 24 biases at
     -75) from the batched GPU quantiser equal the host restatement, and the reconstructed values equal level*delta."""
-    from nerfq_b200 import codec, model as nmodel
+    from nerfq_b200 import codec, deepcabac, model as nmodel
     from oracle import quant_oracle as qo
     torch.manual_seed(0)
     base = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params()
@@ -170,6 +170,8 @@ def test_every_qp_of_the_sweep_bit_exact(dev):
                     got = lv[net][f"{i}.{kind}"].cpu().numpy()
                     assert (got == ref).all(), (qp, net, l, kind)
                     assert (sd[f"{net}.{l}.{kind}"].cpu().numpy() == qo.dequant(ref, q, 2)).all(), (qp, net, l, kind)
+                    host, used_h = deepcabac.host_quant_layer(np.ascontiguousarray(master[f"{net}.{l}.{kind}"].numpy()), 0, 2, q)
+                    assert used_h == q and (got == host).all(), (qp, net, l, kind)      # the host coder consumes identical levels
 
 
 def test_quantizer_non_finite_input_terminates(dev):

@@ -42,7 +42,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out.decode())
     if force or procs or _stale(LIB, objs):
         subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs)
+    build_host(force)
     return LIB
+
+
+HOST_LIB = os.path.join(HERE, "libnncabac.so")
+
+
+def build_host(force: bool = False) -> str:
+    """The host-side NNC coder (include/nncabac.h): plain C++17, no CUDA."""
+    src = os.path.join(HERE, "csrc_host", "nncabac.cpp")
+    hdr = os.path.join(HERE, "..", "include", "nncabac.h")
+    if force or _stale(HOST_LIB, [src, hdr]):
+        subprocess.check_call([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra", "-o", HOST_LIB, src])
+    return HOST_LIB
 
 
 if __name__ == "__main__":

@@ -396,9 +396,14 @@ __global__ void pack_rays_kernel(const CamParams cp, const float* __restrict__ r
 // ---------------------------------------------------------------------------------------------
 // LSA objective: loss = mean((rgb-t)^2) + mean((rgb0-t)^2); gradients 2(rgb-t)/(3N)
 // ---------------------------------------------------------------------------------------------
+// Deterministic: every block leaves its two partial sums in the workspace, the block that arrives last adds them up
+// in block order and ACCUMULATES into loss2 (one thread), then re-arms the arrival counter.
+constexpr int kMseMaxBlocks = 592;
 __global__ void mse_grad_kernel(const float* __restrict__ rgb, const float* __restrict__ rgb0, const float* __restrict__ target,
                                 long long n3, long long n3_norm, float* __restrict__ d_rgb, float* __restrict__ d_rgb0,
-                                float* __restrict__ loss2) {
+                                float* __restrict__ loss2, float* __restrict__ partial, unsigned int* __restrict__ counter) {
+    __shared__ float sh[2][8];
+    __shared__ bool is_last;
     float s0 = 0.f, s1 = 0.f;
     const float k = 2.0f / (float)n3_norm;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long long)gridDim.x * blockDim.x) {
@@ -413,9 +418,28 @@ __global__ void mse_grad_kernel(const float* __restrict__ rgb, const float* __re
         }
     }
     s0 = warp_sum(s0); s1 = warp_sum(s1);
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(loss2 + 0, s0 / (float)n3_norm);
-        atomicAdd(loss2 + 1, s1 / (float)n3_norm);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sh[0][warp] = s0; sh[1][warp] = s1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float b0 = 0.f, b1 = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { b0 += sh[0][w]; b1 += sh[1][w]; }
+        partial[2 * blockIdx.x] = b0;
+        partial[2 * blockIdx.x + 1] = b1;
+        __threadfence();
+        is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        float t0 = 0.f, t1 = 0.f;
+        for (int bk = 0; bk < (int)gridDim.x; ++bk) {
+            t0 += __ldcg(partial + 2 * bk);
+            t1 += __ldcg(partial + 2 * bk + 1);
+        }
+        loss2[0] += t0 / (float)n3_norm;
+        loss2[1] += t1 / (float)n3_norm;
+        *counter = 0u;
     }
 }
 
@@ -504,15 +528,19 @@ extern "C" int nerfq_pack_rays(const float* rays_o, const float* rays_d, long lo
     return launch_ok();
 }
 
-// loss2 must be zeroed by the caller; receives {mse(rgb,t), mse(rgb0,t)}.
+// loss2 is accumulated into ({mse(rgb,t), mse(rgb0,t)} are ADDED): the caller zeroes it.
+extern "C" unsigned long long nerfq_mse_grad_workspace_bytes(void) { return 8ull * kMseMaxBlocks + 16; }
+
 extern "C" int nerfq_mse_grad(const float* rgb, const float* rgb0, const float* target, long long n_rays, long long n_norm, float* d_rgb,
-                              float* d_rgb0, float* loss2, cudaStream_t stream) {
+                              float* d_rgb0, float* loss2, void* workspace, cudaStream_t stream) {
     if (n_rays == 0) return 0;
-    if (!rgb || !target || !d_rgb || !loss2 || (rgb0 && !d_rgb0) || n_rays < 0 || n_norm < 0) return -1;
+    if (!rgb || !target || !d_rgb || !loss2 || !workspace || (rgb0 && !d_rgb0) || n_rays < 0 || n_norm < 0) return -1;
     const long long n3 = n_rays * 3;
     const long long n3_norm = (n_norm > 0 ? n_norm : n_rays) * 3;
     long long blocks = (n3 + 255) / 256;
-    if (blocks > 592) blocks = 592;
-    mse_grad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rgb, rgb0, target, n3, n3_norm, d_rgb, d_rgb0, loss2);
+    if (blocks > kMseMaxBlocks) blocks = kMseMaxBlocks;
+    float* partial = reinterpret_cast<float*>(workspace);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(workspace) + 8ull * kMseMaxBlocks);
+    mse_grad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rgb, rgb0, target, n3, n3_norm, d_rgb, d_rgb0, loss2, partial, counter);
     return launch_ok();
 }

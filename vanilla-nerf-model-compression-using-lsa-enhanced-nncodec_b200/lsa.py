@@ -155,6 +155,7 @@ class LSAStep:
         the parameters; 0 is allowed).  Raises if anything on the path is not capturable; the eager `step` stays usable."""
         self._init_optimizer_state()
         R._DPState.get(self.device)                       # data-parallel scratch exists before the capture
+        ops._mse_workspace(self.device)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):

@@ -36,7 +36,8 @@ _PROTOS = {
                                      _c.c_float, _c.c_longlong, _c.c_longlong, _c.c_void_p, _c.c_void_p]),
     "nerfq_pack_rays": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_float,
                                    _c.c_float, _c.c_void_p, _c.c_void_p]),
-    "nerfq_mse_grad": (_c.c_int, [_c.c_void_p] * 3 + [_c.c_longlong, _c.c_longlong] + [_c.c_void_p] * 4),
+    "nerfq_mse_grad": (_c.c_int, [_c.c_void_p] * 3 + [_c.c_longlong, _c.c_longlong] + [_c.c_void_p] * 5),
+    "nerfq_mse_grad_workspace_bytes": (_c.c_ulonglong, []),
     "nerfq_mlp_backward": (_c.c_int, [_c.c_void_p] * 4 + [_c.c_longlong, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "nerfq_mlp_backward_partial": (_c.c_int, [_c.c_void_p] * 4 + [_c.c_longlong, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "nerfq_mlp_backward_finalize": (_c.c_int, [_c.c_void_p] * 4),
@@ -194,6 +195,17 @@ def pack_rays(rays_o: torch.Tensor, rays_d: torch.Tensor, ndc: bool, H: int, W: 
     return out
 
 
+_MSE_WS = {}
+
+
+def _mse_workspace(dev) -> torch.Tensor:
+    """Per-device scratch of nerfq_mse_grad (zeroed once; the kernel re-arms it).  Calls are stream-ordered."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _MSE_WS:
+        _MSE_WS[key] = torch.zeros(int(L().nerfq_mse_grad_workspace_bytes()), dtype=torch.uint8, device=dev)
+    return _MSE_WS[key]
+
+
 def mse_grad(rgb: torch.Tensor, rgb0: Optional[torch.Tensor], target: torch.Tensor, n_norm: int = 0,
              loss2: Optional[torch.Tensor] = None):
     """(loss2 = [mse(rgb,t), mse(rgb0,t)], d_rgb, d_rgb0) for loss = mse(rgb,t) + mse(rgb0,t).  n_norm: rays the mean runs
@@ -207,8 +219,9 @@ def mse_grad(rgb: torch.Tensor, rgb0: Optional[torch.Tensor], target: torch.Tens
         d_rgb0 = torch.empty_like(rgb0)
     if loss2 is None:
         loss2 = torch.zeros(2, dtype=torch.float32, device=rgb.device)
+    ws = _mse_workspace(rgb.device)
     _lib.check(L().nerfq_mse_grad(rgb.data_ptr(), _p(rgb0), target.data_ptr(), n, int(n_norm), d_rgb.data_ptr(), _p(d_rgb0),
-                                  loss2.data_ptr(), _stream()), "nerfq_mse_grad")
+                                  loss2.data_ptr(), ws.data_ptr(), _stream()), "nerfq_mse_grad")
     return loss2, d_rgb, d_rgb0
 
 
