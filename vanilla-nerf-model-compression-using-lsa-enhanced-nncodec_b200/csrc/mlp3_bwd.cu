@@ -13,7 +13,9 @@
 // scale-gradient sums in registers (no cross-lane reduction), and writes the next GEMM's operand row.  Saved
 // activations are read straight from the forward kernel's chunk-major HBM slots (coalesced 32-byte requests,
 // L2-prefetched two jobs ahead).
-// Gradients are tiny (1e-7..1e-3): each group is multiplied by a power of two that brings max|d_raw| into [8,16)
+// As in the forward kernel, the two 128-point halves of a group are in flight together (own accumulators, barriers and
+// team of 8 epilogue warps; every weight chunk feeds both).
+// Gradients are tiny (1e-7..1e-3): each half-group is multiplied by a power of two that brings max|d_raw| into [8,16)
 // -- backpropagation is linear, the factor is exact and is divided out where the scale-gradient sums are flushed --
 // which keeps fp16's 11-bit significand for the operands without its range problem.
 #include <cuda_fp16.h>
@@ -36,7 +38,7 @@ struct Bwd3Params {
 };
 
 constexpr uint32_t kS3BwdGa = kS3BwdPg + 4096;          // float ga[256]: alpha-head gradient per point
-constexpr uint32_t kS3BwdMax = kS3BwdGa + 1024;         // uint gmax[2], float rinv, int group
+constexpr uint32_t kS3BwdMax = kS3BwdGa + 1024;         // per half (16 bytes each): uint gmax[2], float rinv, int group
 static_assert(kS3BwdMax + 32 <= kS3Misc, "backward scratch must fit the encoding-tile region");
 
 // one 128-byte line into L2
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
     auto bar = [&](int i) { return sbase + kS3Bars + 8u * i; };
 
     {
-        if (threadIdx.x < 2) reinterpret_cast<uint32_t*>(smem + kS3BwdMax)[threadIdx.x] = 0u;
+        if (threadIdx.x < 8) reinterpret_cast<uint32_t*>(smem + kS3BwdMax)[threadIdx.x] = 0u;
     }
     // the CTA owns the SM (1 CTA/SM by shared-memory size) and allocates all 512 TMEM columns, so the allocation starts
     // at column 0; treating the base as a constant frees a register in every epilogue thread
@@ -81,8 +83,8 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
         asm volatile("setmaxnreg.dec.sync.aligned.u32 " NERFQ_REGS_CTRL3 ";");
         if (warp == 0 || warp == 2) {
             loader3(sbase, prm.packed + kOffBwd3Image, kBwd3Chunks, n_iters, warp >> 1);
-        } else if (warp == 1) {
-            if (n_iters > 0) issuer3<kBwd3Jobs, kTrace>(sbase, tmem_base, prm.prog.half, n_iters, false, prm.dbg);
+        } else {
+            if (n_iters > 0) issuer3<false, kTrace>(sbase, tmem_base, n_iters, (uint32_t)(warp >> 1), prm.dbg);
         }
     } else {
         // ================= epilogue warps =================
@@ -95,9 +97,11 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
         // halves its duration; two 8-warp teams running both jobs of a step concurrently measured slower).  A warp owns
         // lane quarter q and point quarter pq (64 points = 4 chunks of 16) of both accumulators.
         const int q = tw & 3, pq = e >> 2;
-        const uint32_t tmem_lane = tmem_base + (uint32_t(q * 32) << 16) + pq * 64;
+        // half-group A (points 0..127: warps e < 8) or B: own accumulators, barriers, gradient scale and scratch
+        const int team = e >> 3, le = e & 7;
+        const uint32_t tmem_lane = tmem_base + (uint32_t(q * 32) << 16) + team * 256 + (pq & 1) * 64;
         const uint32_t act = sbase + kS3Act;
-        const uint32_t pg_a = sbase + kS3BwdPg, ga_a = sbase + kS3BwdGa + 4 * (pq * 64), max_a = sbase + kS3BwdMax;
+        const uint32_t pg_a = sbase + kS3BwdPg, ga_a = sbase + kS3BwdGa + 4 * (pq * 64), max_a = sbase + kS3BwdMax + 16 * team;
         const float2* g_sb = reinterpret_cast<const float2*>(prm.packed + kOffSB);
         const float* g_wa = reinterpret_cast<const float*>(prm.packed + kOffWAlpha);
         const float* g_wr = reinterpret_cast<const float*>(prm.packed + kOffWRgb);
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
         };
         float2 c_next = make_float2(1.f, 0.f);
         if (n_iters > 0) {
-            publish(kB3ActHi);       // D_hi is free at kernel start
+            publish(kB3ActHi + team);       // D_hi is free at kernel start
             c_next = __ldg(&g_sb[prm.prog.job[0].ch + cl]);
         }
         int it = 0;
@@ -168,10 +172,10 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
             // ================= prologue: head gradients, group scale, views-layer gradient =================
             unsigned long long tp0 = 0;
             if (tracing) tp0 = clock64();
-            const int pt = e * 32 + lane;             // warps 0..7 own one point each
+            const int pt = team * (int)kHalfPts3 + le * 32 + lane;             // the first four warps of a team own one point each
             const long long gidx = (long long)g * kGroupPts + pt;
             float4 dr = make_float4(0.f, 0.f, 0.f, 0.f), rw = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e < 8 && gidx < prm.n_points) {
+            if (le < 4 && gidx < prm.n_points) {
                 dr = *reinterpret_cast<const float4*>(prm.d_raw + 4 * gidx);
                 rw = *reinterpret_cast<const float4*>(prm.raw + 4 * gidx);
             }
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 prefetch_seq(g, 2);
             }
             const uint32_t slot_max = max_a + 4 * (it & 1);
-            if (e < 8) {
+            if (le < 4) {
                 float m = fmaxf(fmaxf(fabsf(dr.x), fabsf(dr.y)), fmaxf(fabsf(dr.z), fabsf(dr.w)));
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                     red_global_add_fixed(prm.grad_tmp + kChAlpha, pa);
                 }
             }
-            named_bar_sync3(1, 32 * kEpiWarps3);
+            named_bar_sync3(1 + team, 32 * kTeamWarps3);
             float rscale = 0.0f, rinv = 0.0f;
             {
                 uint32_t mbits;
@@ -216,7 +220,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                     rinv = __int_as_float((ex - 3) << 23);
                 }
             }
-            if (e < 8) {
+            if (le < 4) {
                 const float er = __ldg(&g_sb[kChRgb + 0]).x, eg = __ldg(&g_sb[kChRgb + 1]).x, eb = __ldg(&g_sb[kChRgb + 2]).x;
                 const float ea = __ldg(&g_sb[kChAlpha]).x;
                 st_shared_v4(pg_a + 16 * pt, __float_as_uint(dr.x * rscale * er), __float_as_uint(dr.y * rscale * eg),
@@ -228,12 +232,12 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
             // (one slot is enough: it is rewritten after the next group's first barrier, which every warp reaches only
             // after its last job of this group)
             const uint32_t rinv_a = max_a + 8;
-            if (e == 8 && lane == 0) {
+            if (le == 4 && lane == 0) {
                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(max_a + 4 * ((it & 1) ^ 1)), "r"(0u) : "memory");
                 st_shared_f32(rinv_a, rinv);
                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(max_a + 12), "r"(g) : "memory");      // group index for the job loop (same reason)
             }
-            named_bar_sync3(1, 32 * kEpiWarps3);
+            named_bar_sync3(1 + team, 32 * kTeamWarps3);
 
             // ---- views-layer job: d hv[k][n] = sum_c g_c[n] * w_rgb[c][k], channels 0..127 ----
             if (tracing) { const unsigned long long t = clock64(); t_pro += t - tp0; tp0 = t; }
@@ -260,7 +264,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                     chunk16(dpk, hp.a, hp.b, true, true, row_addr, swz, cc, s1, s2);
                 }
                 // ds * s = sum dY (y - b) = s1 - b * (sum dY)
-                publish(kB3ActLo);
+                publish(kB3ActLo + team);
                 red_global_add_fixed(prm.grad_tmp + kChViews + chh, (s1 - c.y * s2) * ld_shared_f32(rinv_a));
             }
 
@@ -285,12 +289,12 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 if (j + 3 <= kBwd3Jobs) prefetch_seq(gj, j + 3);            // the job after next, into L2 (one line per thread)
                 unsigned long long tj0 = 0;
                 if (tracing) tj0 = clock64();
-                if (hi) { mbar_wait(bar(kB3AccReady + 1), ph_acc1); ph_acc1 ^= 1; }
-                else { mbar_wait(bar(kB3AccReady + 0), ph_acc0); ph_acc0 ^= 1; }
+                if (hi) { mbar_wait(bar(kB3AccReady + 2 * team + 1), ph_acc1); ph_acc1 ^= 1; }
+                else { mbar_wait(bar(kB3AccReady + 2 * team), ph_acc0); ph_acc0 ^= 1; }
                 tc_fence_after_sync();
                 if (tracing) { const unsigned long long t = clock64(); t_acc += t - tj0; tj0 = t; }
                 c_next = __ldg(&g_sb[prm.prog.job[j + 1 < kBwd3Jobs ? j + 1 : 0].ch + cl]);        // in flight during this job
-                const uint32_t ta = tmem_lane + (hi ? 256u : 0u);
+                const uint32_t ta = tmem_lane + (hi ? 128u : 0u);
                 const bool relu = f & JB_RELU, write = !(f & JB_NO_WRITE);
                 float s1 = 0.0f, s2 = 0.0f;
                 uint32_t va[16];
@@ -323,12 +327,12 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
 #pragma unroll
                     for (int i = 0; i < 8; ++i) dpk[i] = cvt_pack_f16(__uint_as_float(va[2 * i]), __uint_as_float(va[2 * i + 1]));
                     if (cc < 3) tmem_ld16(ta + 16 * (cc + 1), va);
-                    if (cc == 0 && (f & JB_WAIT_SF)) { mbar_wait(bar(kB3StageFree + (q >> 1)), ph_sf); ph_sf ^= 1; }
+                    if (cc == 0 && (f & JB_WAIT_SF)) { mbar_wait(bar(kB3StageFree + 2 * team + (q >> 1)), ph_sf); ph_sf ^= 1; }
                     const H32 hp = hh[cc & 1];
                     if (cc < 2) hh[cc & 1] = ldg_nc_32B(hrow + pair_off(cc + 2, swz));       // refill with chunk cc + 2
                     chunk16(dpk, hp.a, hp.b, relu, write, row_addr, swz, cc, s1, s2);
                 }
-                if (write || hi) publish(hi ? kB3ActHi : kB3ActLo);
+                if (write || hi) publish((hi ? kB3ActHi : kB3ActLo) + team);
                 red_global_add_fixed(prm.grad_tmp + jb.ch + cl, (s1 - c.y * s2) * ld_shared_f32(rinv_a));     // after the hand-over
                 if (tracing) t_job += clock64() - tj0;
             }

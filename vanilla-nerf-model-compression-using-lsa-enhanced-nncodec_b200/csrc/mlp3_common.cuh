@@ -1,18 +1,20 @@
 // Device-side pieces shared by the fused MLP kernels (mlp3_fwd.cu, mlp3_bwd.cu):
 // CTA shape, shared-memory map, barrier indices, the weight loader and the MMA-issuing loop.
 #pragma once
+#include <utility>
+
 #include "mlp3_layout.h"
 #include "ptx_sm100.cuh"
 
 namespace nerfq {
 
-// warps 0, 2: weight loaders (warp 0 owns TMEM)   warp 1: MMA issuer   warp 3: idle
+// warps 0, 2: weight loaders (warp 0 owns TMEM)   warps 1, 3: MMA issuers of half A and half B
 // warps 4..19: epilogue; a warp may only touch TMEM lanes 32*(warp % 4).., so warp w owns lane quarter q = w & 3 and
 // point quarter pq = (w - 4) >> 2.
 // Registers: 20 warps are launched with 96 registers each; the control warp group then releases registers
 // (setmaxnreg.dec) and the four epilogue warp groups claim them (setmaxnreg.inc) -- see kRegsCtrl3 / kRegsEpi3.
 constexpr int kCtrlWarps3 = 4;
-#define NERFQ_REGS_CTRL3 "56"
+#define NERFQ_REGS_CTRL3 "64"
 #define NERFQ_REGS_EPI3 "104"
 constexpr int kEpiWarps3 = 16;
 constexpr int kThreads3 = 32 * (kCtrlWarps3 + kEpiWarps3);
@@ -23,19 +25,26 @@ constexpr uint32_t kS3Ring = kS3Act + kAct3Bytes;                // 4 x 16 KB we
 constexpr uint32_t kS3Enc = kS3Ring + kSlots3 * kChunk3Bytes;    // forward: 32 KB encodings; backward: scratch
 constexpr uint32_t kS3Misc = kS3Enc + kEnc3Bytes;                // forward: float[256] alpha sums
 constexpr uint32_t kS3Bars = kS3Misc + 1024;
-constexpr uint32_t kS3TmemPtr = kS3Bars + 8 * 16;
+constexpr uint32_t kS3TmemPtr = kS3Bars + 8 * 24;
 constexpr uint32_t kS3Bytes = kS3TmemPtr + 16 + 1024;            // + slack for the manual 1 KB alignment
 
 // backward: the 32 KB "Enc" region holds  float4 pg[256] (per-point head gradients)  and  float red[2436]
 constexpr uint32_t kS3BwdPg = kS3Enc;
 constexpr uint32_t kS3BwdRed = kS3Enc + 4096;
 
+// Two half-groups of 128 points ("A": points 0..127, "B": 128..255) are in flight per CTA, each with its own pair of
+// accumulators (TMEM columns 256 X + 128 hi ..), its own rows of the operand tiles and its own team of 8 epilogue warps;
+// every weight chunk in the ring feeds A's MMAs and then B's, so the weight traffic per flop is that of one 256-point
+// group.  Barriers below marked [X] exist once per half.
 constexpr int kB3WFull = 0;       // [4]
 constexpr int kB3WEmpty = 4;      // [4]
-constexpr int kB3ActLo = 8;       // 16 arrivals: job for channels 0..127 done (operand written, D_lo drained)
-constexpr int kB3ActHi = 9;
-constexpr int kB3AccReady = 10;   // [2] tcgen05.commit
-constexpr int kB3StageFree = 12;  // [2] tcgen05.commit
+constexpr int kB3ActLo = 8;       // [X] 8 arrivals: job for channels 0..127 done (operand written, D_lo drained)
+constexpr int kB3ActHi = 10;      // [X]
+constexpr int kB3AccReady = 12;   // [X][2] tcgen05.commit
+constexpr int kB3StageFree = 16;  // [X][2] tcgen05.commit
+constexpr int kB3NumBars = 20;
+constexpr int kTeamWarps3 = 8;    // epilogue warps per half
+constexpr uint32_t kHalfPts3 = 128;
 
 __device__ __forceinline__ uint64_t umma_desc_mn3(uint32_t saddr) {     // MN-major SWIZZLE_128B activation tile
     uint64_t d = 0;
@@ -46,7 +55,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn3(uint32_t saddr) {     // MN-ma
     d |= static_cast<uint64_t>(SWZ_128B) << 61;
     return d;
 }
-constexpr uint32_t kIdesc3BK = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);   // f16 x f16 -> f32, M=128, N=256
+constexpr uint32_t kIdesc3BK = (1u << 4) | ((kHalfPts3 >> 3) << 17) | ((128u >> 4) << 24);   // f16 x f16 -> f32, M=128, N=128
 constexpr uint32_t kIdesc3BMN = kIdesc3BK | (1u << 16);                                  // B operand MN-major
 
 __device__ __forceinline__ void named_bar_sync3(int id, int nthreads) {
@@ -54,16 +63,18 @@ __device__ __forceinline__ void named_bar_sync3(int id, int nthreads) {
 }
 
 // ---- one-time setup shared by both kernels; returns the TMEM base -----------------------------------
-__device__ __forceinline__ uint32_t setup3(uint8_t* smem, uint32_t sbase, int warp, int act_arrivals = kEpiWarps3) {
+__device__ __forceinline__ uint32_t setup3(uint8_t* smem, uint32_t sbase, int warp) {
     auto bar = [&](int i) { return sbase + kS3Bars + 8u * i; };
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kSlots3; ++i) { mbar_init(bar(kB3WFull + i), 1); mbar_init(bar(kB3WEmpty + i), 1); }
-        mbar_init(bar(kB3ActLo), act_arrivals);
-        mbar_init(bar(kB3ActHi), act_arrivals);
-        mbar_init(bar(kB3AccReady + 0), 1);
-        mbar_init(bar(kB3AccReady + 1), 1);
-        mbar_init(bar(kB3StageFree + 0), 1);
-        mbar_init(bar(kB3StageFree + 1), 1);
+        for (int i = 0; i < kSlots3; ++i) { mbar_init(bar(kB3WFull + i), 1); mbar_init(bar(kB3WEmpty + i), 2); }      // both issuers release a slot
+        for (int x = 0; x < 2; ++x) {
+            mbar_init(bar(kB3ActLo + x), kTeamWarps3);
+            mbar_init(bar(kB3ActHi + x), kTeamWarps3);
+            mbar_init(bar(kB3AccReady + 2 * x + 0), 1);
+            mbar_init(bar(kB3AccReady + 2 * x + 1), 1);
+            mbar_init(bar(kB3StageFree + 2 * x + 0), 1);
+            mbar_init(bar(kB3StageFree + 2 * x + 1), 1);
+        }
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(sbase + kS3TmemPtr, 512);
@@ -97,109 +108,116 @@ __device__ __forceinline__ void loader3(uint32_t sbase, const uint8_t* img, int 
     }
 }
 
-// ---- MMA issuer: walks the half-step program once per group ------------------------------------------------
+// ---- MMA issuer: walks the half-step program once per group, for ONE half-group ----------------------------
+// Two issuer warps run this, x = 0 (half A) and x = 1 (half B): each waits for its own half's operands, issues its own
+// MMAs (M=128, N=128, K=16; four per weight chunk) into its own accumulators and commits its own barriers, so the two
+// halves drift apart freely -- while one half's epilogue runs, the other half's MMAs keep the tensor pipe busy.  Both
+// read every weight chunk from the same ring slot; a slot is released when both have committed it (WEmpty counts 2).
 // Called by a whole converged warp: every lane waits, one elected lane issues the MMAs and commits, and all operands
-// are warp-uniform so they live in uniform registers.  The tensor pipe queues only ~2 MMAs, so the code between the
-// last MMA of a chunk and the first MMA of the next (commit, ring wait, descriptor bump) has to stay short.
+// are warp-uniform so they live in uniform registers.
+// The issuer shares its scheduler with four busy epilogue warps, so every instruction between two chunks costs several
+// cycles of tensor-pipe idle time (measured: the table-driven loop of round 1 spent ~700 cycles per 512-cycle chunk).
+// The walk is therefore GENERATED from the compile-time program (kProg3FwdC / kProg3BwdC): one straight-line block
+// per chunk in which flags, operand offsets and barrier choices are constants -- a ring-slot computation, at most one
+// operand wait, four MMAs and one to three commits.
 // `first_lo_wait`: the forward kernel's first group waits for the initial encodings (later groups get them with the
 // ActLo arrival the rgb step already consumed).
-// kTrace: accumulate cycle counters {total, wait WFull, wait ActLo, wait ActHi} into dbg[8*blockIdx.x + 0..3].
-template <int kHalves, bool kTrace = false>
-__device__ __forceinline__ void issuer3(uint32_t sbase, uint32_t tmem_base, const Half3* __restrict__ prog, int n_iters,
-                                        bool first_lo_wait, unsigned long long* dbg = nullptr) {
-    unsigned long long t_w = 0, t_lo = 0, t_hi = 0, t_begin = 0;
+// kTrace: accumulate cycle counters {total, wait WFull, wait ActLo, wait ActHi} into dbg[8*blockIdx.x + 0..3] (x = 0 only).
+struct Issuer3State {
+    uint32_t bar0, bar_lo, bar_hi, tmem_x, seq, ph_lo, ph_hi;
+    uint64_t a_desc0, b_act0, b_enc0;
+    bool slot_probed;                      // the previous chunk already saw this chunk's weights in the ring
+    unsigned long long t_w, t_lo, t_hi;
+};
+
+template <bool kFwd, int H> constexpr Half3 half3_of() { return kFwd ? kProg3FwdC.half[H < kFwd3Jobs ? H : 0] : kProg3BwdC.half[H < kBwd3Jobs ? H : 0]; }
+
+template <bool kTrace> __device__ __forceinline__ void issuer_wait3(uint32_t bar, uint32_t& ph, unsigned long long& acc) {
+    unsigned long long t0 = 0;
+    if (kTrace) t0 = clock64();
+    mbar_wait(bar, ph);
+    ph ^= 1;
+    tc_fence_after_sync();
+    if (kTrace) acc += clock64() - t0;
+}
+
+// one weight chunk of half-step H: chunk J (activation chunks first, then the encoding chunk)
+template <bool kFwd, int H, int J, bool kTrace> __device__ __forceinline__ void issuer_chunk3(Issuer3State& s, uint32_t x) {
+    constexpr Half3 hs = half3_of<kFwd, H>();
+    constexpr uint32_t f = hs.flags;
+    constexpr bool enc = J >= hs.n_act;
+    constexpr bool last = J + 1 == hs.n_act + (hs.n_enc ? 1 : 0);
+    constexpr uint32_t hi = (f & HS_ACC_HI) ? 1u : 0u;
+    constexpr uint32_t idesc = enc ? kIdesc3BK : kIdesc3BMN;
+    constexpr uint32_t kstep = enc ? (32u >> 4) : ((2u * kKGroup3) >> 4);
+    constexpr uint32_t stage = enc ? (64u >> 4) : ((4u * kKGroup3) >> 4);
+    if (J == 0 && (f & HS_WAIT_LO)) issuer_wait3<kTrace>(s.bar_lo, s.ph_lo, s.t_lo);
+    if (J == 0 && (f & HS_WAIT_HI_AT0)) issuer_wait3<kTrace>(s.bar_hi, s.ph_hi, s.t_hi);
+    if (J == 2 && !enc && (f & HS_WAIT_HI_AT2)) issuer_wait3<kTrace>(s.bar_hi, s.ph_hi, s.t_hi);
+    const uint32_t slot = s.seq & (kSlots3 - 1), par = (s.seq >> 2) & 1;
+    ++s.seq;
+    if (!s.slot_probed) {
+        unsigned long long t0 = 0;
+        if (kTrace) t0 = clock64();
+        mbar_wait(s.bar0 + 8 * (kB3WFull + slot), par);
+        if (kTrace) s.t_w += clock64() - t0;
+    }
+    tc_fence_after_sync();
+    // (the operand bases pass through an empty asm: without it the compiler hoists the ~100 distinct descriptors of a
+    // group out of the group loop and spills them -- a local-memory reload costs ~1000 cycles with this shared-memory carve-out)
+    uint64_t b0 = enc ? s.b_enc0 : s.b_act0;
+    asm volatile("" : "+l"(b0));
+    const uint64_t ad = s.a_desc0 + slot * (kChunk3Bytes >> 4);
+    const uint64_t b = enc ? b0 : b0 + (uint32_t)J * ((8u * kKGroup3) >> 4);
+    uint32_t d_tmem = s.tmem_x + 128u * hi;
+    asm volatile("" : "+r"(d_tmem));
+    if (elect_one()) {
+        umma_ss(d_tmem, ad, b, idesc, J > 0 ? 1u : 0u);
+        umma_ss(d_tmem, ad + 2, b + kstep, idesc, 1u);
+    }
+    __syncwarp();
+    // while the first MMAs run: is the NEXT chunk already in the ring?  (takes the barrier wait out of the gap between chunks)
+    s.slot_probed = __all_sync(0xffffffffu, mbar_test_wait(s.bar0 + 8 * (kB3WFull + (s.seq & (kSlots3 - 1))), (s.seq >> 2) & 1));
+    if (elect_one()) {
+        umma_ss(d_tmem, ad + (kStage3Bytes >> 4), b + stage, idesc, 1u);
+        umma_ss(d_tmem, ad + (kStage3Bytes >> 4) + 2, b + stage + kstep, idesc, 1u);
+        umma_commit(s.bar0 + 8 * (kB3WEmpty + slot));
+        if (!enc && (f & HS_SF) && J < 2) umma_commit(s.bar0 + 8 * (kB3StageFree + J) + 16 * x);
+        if (last) umma_commit(s.bar0 + 8 * (kB3AccReady + hi) + 16 * x);
+    }
+    __syncwarp();
+}
+template <bool kFwd, int H, bool kTrace, int... Js> __device__ __forceinline__ void issuer_half3(Issuer3State& s, uint32_t x, std::integer_sequence<int, Js...>) {
+    (issuer_chunk3<kFwd, H, Js, kTrace>(s, x), ...);
+}
+template <bool kFwd, bool kTrace, int... Hs> __device__ __forceinline__ void issuer_group3(Issuer3State& s, uint32_t x, std::integer_sequence<int, Hs...>) {
+    (issuer_half3<kFwd, Hs, kTrace>(s, x, std::make_integer_sequence<int, half3_of<kFwd, Hs>().n_act + (half3_of<kFwd, Hs>().n_enc ? 1 : 0)>{}), ...);
+}
+
+template <bool kFwd, bool kTrace = false>
+__device__ __forceinline__ void issuer3(uint32_t sbase, uint32_t tmem_base, int n_iters, uint32_t x, unsigned long long* dbg = nullptr) {
+    unsigned long long t_begin = 0;
     if (kTrace) t_begin = clock64();
-    const uint32_t bar0 = sbase + kS3Bars;
-    const uint64_t a_desc0 = umma_smem_desc(sbase + kS3Ring, 512, SWZ_64B);
-    const uint64_t b_act0 = umma_desc_mn3(sbase + kS3Act);
-    const uint64_t b_enc0 = umma_smem_desc(sbase + kS3Enc, 1024, SWZ_128B);
-    uint32_t seq = 0, ph_lo = 0, ph_hi = 0;
-    bool slot_probed = false;          // the previous chunk already saw this chunk's weights in the ring
-    // one weight chunk: 4 MMAs; stage 1 of the B operand starts `stage` (16-byte units) after stage 0, the second
-    // K=16 half of a stage `kstep` after the first.  The tensor pipe queues ~2 MMAs, so after the first two the issue
-    // of the third blocks until the first retires: that time is used to probe the NEXT chunk's "slot full" barrier,
-    // which takes the ~130-cycle barrier wait out of the gap between chunks whenever the loader is ahead.
-    auto chunk = [&](uint32_t d_tmem, uint64_t b, uint32_t idesc, uint32_t kstep, uint32_t stage, uint32_t accumulate,
-                     uint32_t commit_a, uint32_t commit_b) {
-        const uint32_t slot = seq & (kSlots3 - 1), par = (seq >> 2) & 1;
-        ++seq;
-        if (!slot_probed) {
-            unsigned long long t0 = 0;
-            if (kTrace) t0 = clock64();
-            mbar_wait(bar0 + 8 * (kB3WFull + slot), par);
-            if (kTrace) t_w += clock64() - t0;
-        }
-        tc_fence_after_sync();
-        const uint64_t ad = a_desc0 + slot * (kChunk3Bytes >> 4);
-        if (elect_one()) {
-            umma_ss(d_tmem, ad, b, idesc, accumulate);
-            umma_ss(d_tmem, ad + 2, b + kstep, idesc, 1u);
-        }
-        __syncwarp();
-        slot_probed = __all_sync(0xffffffffu, mbar_test_wait(bar0 + 8 * (kB3WFull + (seq & (kSlots3 - 1))), (seq >> 2) & 1));
-        if (elect_one()) {
-            umma_ss(d_tmem, ad + (kStage3Bytes >> 4), b + stage, idesc, 1u);
-            umma_ss(d_tmem, ad + (kStage3Bytes >> 4) + 2, b + stage + kstep, idesc, 1u);
-            umma_commit(bar0 + 8 * (kB3WEmpty + slot));
-            if (commit_a) umma_commit(commit_a);
-            if (commit_b) umma_commit(commit_b);
-        }
-        __syncwarp();
-    };
-    if (first_lo_wait) {
-        mbar_wait(bar0 + 8 * kB3ActLo, ph_lo);
-        ph_lo ^= 1;
-        tc_fence_after_sync();
-    }
-    for (int it = 0; it < n_iters; ++it) {
+    Issuer3State s;
+    s.bar0 = sbase + kS3Bars;
+    s.bar_lo = s.bar0 + 8 * (kB3ActLo + x);
+    s.bar_hi = s.bar0 + 8 * (kB3ActHi + x);
+    s.tmem_x = tmem_base + 256u * x;
+    s.seq = s.ph_lo = s.ph_hi = 0;
+    s.slot_probed = false;
+    s.t_w = s.t_lo = s.t_hi = 0;
+    // half B: 128 points further along N -- two 64-point blocks of the MN-major tile, 128 rows of the K-major tile
+    s.a_desc0 = umma_smem_desc(sbase + kS3Ring, 512, SWZ_64B);
+    s.b_act0 = umma_desc_mn3(sbase + kS3Act) + (x ? ((2u * kNGroup3) >> 4) : 0u);
+    s.b_enc0 = umma_smem_desc(sbase + kS3Enc, 1024, SWZ_128B) + (x ? ((kHalfPts3 * 128u) >> 4) : 0u);
+    if (kFwd) issuer_wait3<kTrace>(s.bar_lo, s.ph_lo, s.t_lo);      // first group's encodings
 #pragma unroll 1
-        for (int h = 0; h < kHalves; ++h) {
-            const Half3 hs = prog[h];
-            const uint32_t f = hs.flags;
-            const uint32_t hi = f & HS_ACC_HI;
-            const uint32_t d_tmem = tmem_base + (hi ? 256u : 0u);
-            const uint32_t acc_bar = bar0 + 8 * (kB3AccReady + (hi ? 1 : 0));
-            if (f & HS_WAIT_LO) {
-                unsigned long long t0 = 0;
-                if (kTrace) t0 = clock64();
-                mbar_wait(bar0 + 8 * kB3ActLo, ph_lo);
-                ph_lo ^= 1;
-                tc_fence_after_sync();
-                if (kTrace) t_lo += clock64() - t0;
-            }
-            if (f & HS_WAIT_HI_AT0) {
-                unsigned long long t0 = 0;
-                if (kTrace) t0 = clock64();
-                mbar_wait(bar0 + 8 * kB3ActHi, ph_hi);
-                ph_hi ^= 1;
-                tc_fence_after_sync();
-                if (kTrace) t_hi += clock64() - t0;
-            }
-            const int n_act = hs.n_act, n_enc = hs.n_enc;
-            uint64_t b = b_act0;
-#pragma unroll 1
-            for (int j = 0; j < n_act; ++j) {
-                if (j == 2 && (f & HS_WAIT_HI_AT2)) {
-                    unsigned long long t0 = 0;
-                    if (kTrace) t0 = clock64();
-                    mbar_wait(bar0 + 8 * kB3ActHi, ph_hi);
-                    ph_hi ^= 1;
-                    tc_fence_after_sync();
-                    if (kTrace) t_hi += clock64() - t0;
-                }
-                const uint32_t sf = ((f & HS_SF) && j < 2) ? bar0 + 8 * (kB3StageFree + j) : 0u;
-                const uint32_t done = (j + 1 == n_act && n_enc == 0) ? acc_bar : 0u;
-                chunk(d_tmem, b, kIdesc3BMN, (2u * kKGroup3) >> 4, (4u * kKGroup3) >> 4, j > 0 ? 1u : 0u, sf, done);
-                b += (8u * kKGroup3) >> 4;
-            }
-            if (n_enc) chunk(d_tmem, b_enc0, kIdesc3BK, 32u >> 4, 64u >> 4, n_act > 0 ? 1u : 0u, 0u, acc_bar);
-        }
-    }
-    if (kTrace && dbg && (threadIdx.x & 31) == 0) {
+    for (int it = 0; it < n_iters; ++it) issuer_group3<kFwd, kTrace>(s, x, std::make_integer_sequence<int, kFwd ? kFwd3Jobs : kBwd3Jobs>{});
+    if (kTrace && dbg && x == 0 && (threadIdx.x & 31) == 0) {
         dbg[8 * blockIdx.x + 0] = clock64() - t_begin;
-        dbg[8 * blockIdx.x + 1] = t_w;
-        dbg[8 * blockIdx.x + 2] = t_lo;
-        dbg[8 * blockIdx.x + 3] = t_hi;
+        dbg[8 * blockIdx.x + 1] = s.t_w;
+        dbg[8 * blockIdx.x + 2] = s.t_lo;
+        dbg[8 * blockIdx.x + 3] = s.t_hi;
     }
 }
 

@@ -6,11 +6,15 @@
 //   NeRF.forward with ScaledLinear layers           utils.py:57-80, transforms.py:104-111
 // Output: raw[M,4] = (rgb logits, sigma) as run_network returns it (run_nerf.py:61-63).
 //
-// One persistent CTA per SM iterates over groups of 256 points (mlp3_layout.h).  Per layer the tensor cores compute
+// One persistent CTA per SM iterates over groups of 256 points (mlp3_layout.h), processed as two independent halves of
+// 128 points that are in flight together: per layer and half the tensor cores compute
 //   D[o][n] = sum_k L[o][k] * X[n][k]      (L = integer weight levels, fp16; X = activations, fp16; D fp32 in TMEM)
-// as two accumulators of 128 output channels x 256 points; 16 KB weight chunks stream from L2 through a 4-slot
-// ring of bulk async copies, the activation tile stays in shared memory and is rewritten in place.  Each of the
-// 16 epilogue warps owns 32 output channels (its TMEM lanes) x 64 points of every accumulator: a thread keeps the
+// as two accumulators of 128 output channels x 128 points (four accumulators = all 512 TMEM columns); 16 KB weight
+// chunks stream from L2 through a 4-slot ring of bulk async copies and each chunk feeds half A's MMAs, then half B's;
+// the activation tile stays in shared memory and is rewritten in place.  A half has its own team of 8 epilogue warps and
+// its own barriers, so while one half's epilogue runs (the tensor pipe has nothing to do for THAT half: the next layer
+// needs its output) the pipe works on the other half.  Each epilogue
+// warp owns 32 output channels (its TMEM lanes) x 64 points of its half's accumulators: a thread keeps the
 // dequantisation constants of ITS channel in registers and applies  y = acc * (delta * s[o]) + b[o], ReLU, fp16
 // conversion, storing 8 points per 16-byte shared-memory store into the next layer's operand tile.  The epilogue of
 // channels 0..127 overlaps the MMAs of channels 128..255 and vice versa.  The alpha head is reduced on CUDA cores
@@ -64,13 +68,14 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
 
     if (warp == 0 || warp == 2) {
         loader3(sbase, prm.packed + kOffFwd3Image, kFwd3Chunks, n_iters, warp >> 1);
-    } else if (warp == 1) {
-        if (n_iters > 0) issuer3<kFwd3Jobs, kTrace>(sbase, tmem_base, prm.prog.half, n_iters, true, prm.dbg);
+    } else if (warp == 1 || warp == 3) {
+        if (n_iters > 0) issuer3<true, kTrace>(sbase, tmem_base, n_iters, (uint32_t)(warp >> 1), prm.dbg);
     } else if (warp >= kCtrlWarps3) {
         // ================= epilogue warps =================
         const int e = warp - kCtrlWarps3;
         const int q = warp & 3, pq = e >> 2;
-        const uint32_t tmem_lane = tmem_base + (uint32_t(q * 32) << 16) + pq * 64;
+        const int team = e >> 3;                  // half-group A (points 0..127) or B (128..255): own accumulators and barriers
+        const uint32_t tmem_lane = tmem_base + (uint32_t(q * 32) << 16) + team * 256 + (pq & 1) * 64;
         const uint32_t act = sbase + kS3Act;      // shared-space addresses
         const uint32_t enc = sbase + kS3Enc;
         const uint32_t out_sa = sbase + kS3Misc;
@@ -117,8 +122,8 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
         if (n_iters > 0) {
             load_point(first, vd);
             write_pe_half(enc, pt, role, p);
-            publish(kB3ActLo);        // initial encodings
-            publish(kB3ActHi);        // D_hi is free at kernel start
+            publish(kB3ActLo + team);        // initial encodings
+            publish(kB3ActHi + team);        // D_hi is free at kernel start
             load_consts(0, c_next, wa_next);
         }
         for (int g = first; g < prm.n_groups; g += stride) {
@@ -135,11 +140,11 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                 const float wa = wa_next;
                 unsigned long long t0 = 0;
                 if (tracing) t0 = clock64();
-                if (f & JB_ACC_HI) { mbar_wait(bar(kB3AccReady + 1), ph_acc1); ph_acc1 ^= 1; }
-                else { mbar_wait(bar(kB3AccReady + 0), ph_acc0); ph_acc0 ^= 1; }
+                if (f & JB_ACC_HI) { mbar_wait(bar(kB3AccReady + 2 * team + 1), ph_acc1); ph_acc1 ^= 1; }
+                else { mbar_wait(bar(kB3AccReady + 2 * team), ph_acc0); ph_acc0 ^= 1; }
                 tc_fence_after_sync();
                 if (tracing) { const unsigned long long t1 = clock64(); t_acc += t1 - t0; t0 = t1; }
-                const uint32_t ta = tmem_lane + ((f & JB_ACC_HI) ? 256u : 0u);
+                const uint32_t ta = tmem_lane + ((f & JB_ACC_HI) ? 128u : 0u);
                 load_consts(j + 1 < kFwd3Jobs ? j + 1 : 0, c_next, wa_next);    // in flight during this job
 
                 if (f & JB_FINAL) {
@@ -168,7 +173,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                             if (gi < prm.n_points) prm.raw[4 * gi + 3] = sg;
                         }
                     }
-                    publish(kB3ActHi);
+                    publish(kB3ActHi + team);
                     if (tracing) { const unsigned long long dt = clock64() - t0; t_job += dt; if (j == j_sel) t_sel += dt; }
                     continue;
                 }
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                         if (f & JB_WAIT_SF) {
                             unsigned long long t1 = 0;
                             if (tracing) t1 = clock64();
-                            mbar_wait(bar(kB3StageFree + (q >> 1)), ph_sf);
+                            mbar_wait(bar(kB3StageFree + 2 * team + (q >> 1)), ph_sf);
                             ph_sf ^= 1;
                             if (tracing) t_sf += clock64() - t1;
                         }
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                         for (int k = 0; k < 3; ++k) vd[k] = vd_next[k];
                     }
                 }
-                publish(hi ? kB3ActHi : kB3ActLo);
+                publish((hi ? kB3ActHi : kB3ActLo) + team);
                 if (kSave && kSaveInJob < 4) {
                     // The SM's store path to L2 (~30 B/clk) is the limit while a job runs, and idle while the warps wait for
                     // the next accumulator: the last chunks' saved activations are read back from the operand tile (only this

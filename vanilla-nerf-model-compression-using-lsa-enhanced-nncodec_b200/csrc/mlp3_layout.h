@@ -147,7 +147,7 @@ struct Prog3Bwd {
 //   ActLo arrivals per group: jobs (s,0) for s = 0..9        waits: first chunk of steps 1..10
 //   ActHi arrivals per group: jobs (s,1) for s = 0..8, rgb   waits: chunk 2 of steps 1..9, first hi chunk of step 0
 // (the steps with HS_WAIT_HI_AT2 all have >= 3 activation chunks)
-inline Prog3Fwd make_prog3_fwd() {
+constexpr Prog3Fwd make_prog3_fwd() {
     Prog3Fwd p{};
     int h = 0;
     for (int s = 0; s < kFwd3Steps; ++s) {
@@ -191,7 +191,7 @@ inline Prog3Fwd make_prog3_fwd() {
 // that arrives on ActLo; jobs of step t write the operand of step t+1.
 //   ActLo arrivals per group: prologue, jobs (t,0) for t = 0..7   waits: first chunk of steps 0..8
 //   ActHi arrivals per group: jobs (t,1) for t = 0..8             waits: chunk 2 of steps 1..8, first hi chunk of step 0
-inline Prog3Bwd make_prog3_bwd() {
+constexpr Prog3Bwd make_prog3_bwd() {
     Prog3Bwd p{};
     int h = 0;
     for (int s = 0; s < kBwd3Steps; ++s) {
@@ -231,6 +231,10 @@ inline Prog3Bwd make_prog3_bwd() {
     p.slice_off[0] = 9u * (16 * 256 * 32);
     return p;
 }
+
+// the programs as compile-time constants: the MMA issuers are generated from them (mlp3_common.cuh, issuer3)
+constexpr Prog3Fwd kProg3FwdC = make_prog3_fwd();
+constexpr Prog3Bwd kProg3BwdC = make_prog3_bwd();
 
 // ---- packed network buffer: weight images after the small fields of net_layout.h -----------------
 constexpr size_t kOffFwd3Image = (kPackedBytes + 1023) / 1024 * 1024;

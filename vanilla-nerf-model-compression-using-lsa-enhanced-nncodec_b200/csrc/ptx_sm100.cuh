@@ -63,13 +63,15 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
 #ifndef NERFQ_MBAR_SPIN_LIMIT
 #define NERFQ_MBAR_SPIN_LIMIT (1u << 20)
 #endif
+[[noreturn]] static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {        // cold and out of line: the wait sites stay small
+    printf("nerfq: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+    __trap();
+    __builtin_unreachable();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (threadIdx.x < 128 ? NERFQ_MBAR_SPIN_LIMIT / 8 : NERFQ_MBAR_SPIN_LIMIT)) {   // control warps report first
-            printf("nerfq: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-            __trap();
-        }
+        if (++spins > (threadIdx.x < 128 ? NERFQ_MBAR_SPIN_LIMIT / 8 : NERFQ_MBAR_SPIN_LIMIT)) mbar_timeout(bar, parity);   // control warps report first
     }
 }
 
