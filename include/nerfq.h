@@ -140,6 +140,29 @@ int nerfq_camera_rays(int H, int W, const float* K4, const float* c2w12, int ndc
 int nerfq_pack_rays(const float* rays_o, const float* rays_d, long long n, int ndc, int H, int W, float focal, float near,
                     float far, float* rays_out, nerfq_stream_t stream);
 
+/* render_rays, forward only, as one call (run_nerf.py:348-457 with perturb = 0 and raw_noise_std = 0 -- the test-view
+ * path of render_path, run_nerf.py:161-211): stratified depths -> MLP(coarse) -> composite -> sample_pdf + sort -> MLP(fine)
+ * -> composite, enqueued back to back on `stream`.  rays [n_rays,11]; outputs rgb [n,3], disp [n], acc [n] and, when
+ * Ni > 0, rgb0 / disp0 / acc0 / z_std (z_std nullable).  packed_fine == NULL uses the coarse network for the fine pass
+ * (N_importance > 0 without network_fine).  workspace: nerfq_render_rays_workspace_bytes(n_rays, S, Ni) bytes holding the
+ * depths, raw network outputs and coarse weights between the launches (at the reference's chunk of 32768 rays 137 MB). */
+unsigned long long nerfq_render_rays_workspace_bytes(long long n_rays, int S, int Ni);
+int nerfq_render_rays_fwd(const void* packed_coarse, const void* packed_fine, const float* rays, long long n_rays, int S, int Ni,
+                          int lindisp, int white_bkgd, void* workspace, float* rgb, float* disp, float* acc, float* rgb0,
+                          float* disp0, float* acc0, float* z_std, int max_ctas, nerfq_stream_t stream);
+
+/* to8b, run_nerf_helpers.py:14: out[i] = (uint8)(255 * clip(x[i], 0, 1)), truncating like numpy's astype. */
+int nerfq_to8b(const float* x, uint8_t* out, long long n, nerfq_stream_t stream);
+
+/* Training-batch selection (run_nerf.py:690-735: np.random.choice(H*W, N_rand, replace=False), then rays and target
+ * colours of those pixels): n DISTINCT pixels of one H x W image chosen by a keyed permutation of (seed, step), their
+ * packed rays generated from the pose (as nerfq_camera_rays) and their colours gathered from image [H*W,3] -- one launch,
+ * no host random numbers, no synchronisation.  K4 / c2w12 HOST pointers; image and target_out nullable together;
+ * index_out [n] nullable.  The permutation is this library's own (the reference's host RNG stream is not reproduced). */
+int nerfq_select_batch(int H, int W, const float* K4, const float* c2w12, int ndc, float near, float far, const float* image,
+                       unsigned long long seed, unsigned long long step, long long n, float* rays_out, float* target_out,
+                       int* index_out, nerfq_stream_t stream);
+
 /* img2mse (x2) and gradient, run_nerf_helpers.py:12 and run_nerf.py:741-751.  The two means are ADDED to loss2[2] (the
  * caller zeroes it; several calls accumulate a chunked batch) by one thread in a fixed order: bit-reproducible.
  * n_norm: the number of rays the mean runs over (0 = n_rays); a data-parallel rank passes the GLOBAL batch size so that

@@ -13,7 +13,7 @@ from typing import Dict
 
 import torch
 
-from . import ops
+from . import ops, packed
 from .model import NeRF
 
 
@@ -88,3 +88,44 @@ def apply_lsa(wrapper):
     for net in (out.model, out.model_fine):
         net.set_quant_levels(None, None)
     return out
+
+
+@torch.no_grad()
+def load_levels(wrapper, levels: Dict[str, "torch.Tensor"], qps: Dict[str, int], qp_density: int = 2):
+    """Decoder side (nnc_core/approximator/__init__.py:276-318 `rec` + `apply_lsa`, nnc/compression.py:636-659) without the
+    float detour: the decoded integer levels go straight into the packed networks.
+
+    levels   {state_dict name: int32 tensor or numpy array}: '<layer>.weight', '<layer>.bias' and, for an LSA bitstream,
+             '<layer>.weight_scaling' -- what Decoder.decodeLayer produced
+    qps      {same names: qp actually used} (the iae_v field in front of each tensor, coder/baseline.py:31-34)
+
+    Weight levels become the MLP kernels' integer operands (model.NeRF.set_quant_levels); biases and scales are
+    dequantised (level * delta, one kernel each) into the module's parameters; the float `weight` parameters are set to
+    level * delta so state_dict() equals what the reference's `rec` yields.  The wrapper must carry LSA parameters when the
+    bitstream has scales; they are applied in the MLP epilogue, i.e. the reconstruction equals apply_lsa's
+    `w * ls` up to the fp16 rounding apply_lsa's folded weights would get as operands."""
+    import numpy as np
+    dev = next(wrapper.parameters()).device
+    sd = wrapper.state_dict()
+
+    def as_dev(x):
+        t = torch.from_numpy(np.ascontiguousarray(x)) if not torch.is_tensor(x) else x
+        return t.to(device=dev, dtype=torch.int32).contiguous()
+
+    for prefix, net in (("model", wrapper.model), ("model_fine", wrapper.model_fine)):
+        lv_w, steps = [], []
+        for name, layer in zip(packed.LAYER_NAMES, net.layers()):
+            key = f"{prefix}.{name}"
+            lw = as_dev(levels[key + ".weight"]).reshape(layer.weight.shape)
+            qw = int(qps[key + ".weight"])
+            lv_w.append(lw)
+            steps.append(ops.stepsize(qw, qp_density))
+            layer.weight.copy_(ops.dequantize(lw, qw, qp_density))
+            layer.bias.copy_(ops.dequantize(as_dev(levels[key + ".bias"]), int(qps[key + ".bias"]), qp_density).reshape(layer.bias.shape))
+            ls_key = key + ".weight_scaling"
+            if ls_key in levels:
+                if ls_key not in sd:
+                    raise ValueError(f"the bitstream carries {ls_key} but the wrapper has no LSA parameters (model.LSA(w).add_lsa_params())")
+                layer.weight_scaling.copy_(ops.dequantize(as_dev(levels[ls_key]), int(qps[ls_key]), qp_density).reshape(layer.weight_scaling.shape))
+        net.set_quant_levels(lv_w, steps)
+    return wrapper

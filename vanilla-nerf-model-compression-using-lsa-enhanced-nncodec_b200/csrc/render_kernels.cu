@@ -443,6 +443,84 @@ __global__ void mse_grad_kernel(const float* __restrict__ rgb, const float* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// image output: to8b (run_nerf_helpers.py:14), 4 pixels' worth of channels per thread
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned to8b_one(float x) {
+    // (255 * np.clip(x, 0, 1)).astype(np.uint8): truncation toward zero; NaN -> 0 (numpy's cast of NaN is unspecified,
+    // CUDA's cvt gives 0)
+    const float c = fminf(fmaxf(x, 0.0f), 1.0f);
+    return (unsigned)__float2int_rz(__fmul_rn(255.0f, c));
+}
+__global__ void to8b_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, long long n) {
+    const long long n4 = n >> 2;
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) | (reinterpret_cast<uintptr_t>(out) & 3)) == 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        uint32_t* o4 = reinterpret_cast<uint32_t*>(out);
+        for (long long i = tid; i < n4; i += stride) {
+            const float4 v = x4[i];
+            o4[i] = to8b_one(v.x) | (to8b_one(v.y) << 8) | (to8b_one(v.z) << 16) | (to8b_one(v.w) << 24);
+        }
+        for (long long i = (n4 << 2) + tid; i < n; i += stride) out[i] = (uint8_t)to8b_one(x[i]);
+    } else {
+        for (long long i = tid; i < n; i += stride) out[i] = (uint8_t)to8b_one(x[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// training-batch selection on the device (run_nerf.py:690-735): n distinct pixels of one H x W image, their rays generated
+// from the pose and their target colours gathered, in one launch.
+// The reference draws  np.random.choice(H*W, N_rand, replace=False)  on the host every step; here pixel k of the batch
+// is  perm(k)  for a keyed bijection of [0, H*W): a 4-round Feistel network over the next power of four with cycle
+// walking -- distinct by construction, a fresh permutation per (seed, step), no host work and no synchronisation.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {        // murmur3 finaliser
+    x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t feistel_perm(uint32_t idx, uint32_t n, int half_bits, uint32_t k0, uint32_t k1) {
+    const uint32_t mask = (1u << half_bits) - 1u;
+    uint32_t v = idx;
+    do {                                                         // cycle walking: expected < 4 rounds (domain < 4 n)
+        uint32_t l = v >> half_bits, r = v & mask;
+#pragma unroll
+        for (int round = 0; round < 4; ++round) {
+            const uint32_t f = mix32(r ^ k0 ^ (0x9e3779b9u * (uint32_t)(round + 1)) ^ (k1 << round)) & mask;
+            const uint32_t nl = r;
+            r = l ^ f;
+            l = nl;
+        }
+        v = (l << half_bits) | r;
+    } while (v >= n);
+    return v;
+}
+__global__ void select_batch_kernel(const CamParams cp, const float* __restrict__ image, uint32_t n_pix, int half_bits, uint32_t k0,
+                                    uint32_t k1, long long n, float* __restrict__ rays_out, float* __restrict__ target_out,
+                                    int* __restrict__ index_out) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t pix = feistel_perm((uint32_t)k, n_pix, half_bits, k0, k1);
+    const int j = (int)(pix / (uint32_t)cp.W), i = (int)(pix - (uint32_t)j * (uint32_t)cp.W);
+    const float dx = __fdiv_rn(__fsub_rn((float)i, cp.cx), cp.fx);
+    const float dy = -__fdiv_rn(__fsub_rn((float)j, cp.cy), cp.fy);
+    float o[3], d[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        d[r] = __fadd_rn(__fadd_rn(__fmul_rn(dx, cp.c2w[4 * r + 0]), __fmul_rn(dy, cp.c2w[4 * r + 1])), __fmul_rn(-1.0f, cp.c2w[4 * r + 2]));
+        o[r] = cp.c2w[4 * r + 3];
+    }
+    finish_ray(o, d, cp, rays_out + k * 11);
+    if (target_out) {
+        target_out[3 * k + 0] = image[3ll * pix + 0];
+        target_out[3 * k + 1] = image[3ll * pix + 1];
+        target_out[3 * k + 2] = image[3ll * pix + 2];
+    }
+    if (index_out) index_out[k] = (int)pix;
+}
+
 }  // namespace nerfq
 
 // ---------------------------------------------------------------------------------------------
@@ -543,4 +621,80 @@ extern "C" int nerfq_mse_grad(const float* rgb, const float* rgb0, const float* 
     unsigned int* counter = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(workspace) + 8ull * kMseMaxBlocks);
     mse_grad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rgb, rgb0, target, n3, n3_norm, d_rgb, d_rgb0, loss2, partial, counter);
     return launch_ok();
+}
+
+extern "C" int nerfq_to8b(const float* x, uint8_t* out, long long n, cudaStream_t stream) {
+    if (n == 0) return 0;
+    if (!x || !out || n < 0) return -1;
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    to8b_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, out, n);
+    return launch_ok();
+}
+
+// K4 / c2w12 are HOST pointers; image [H*W,3] (nullable together with target_out), rays_out [n,11], target_out [n,3],
+// index_out [n] (nullable): the pixel indices chosen.  n <= H*W.
+extern "C" int nerfq_select_batch(int H, int W, const float* K4, const float* c2w12, int ndc, float near, float far, const float* image,
+                                  unsigned long long seed, unsigned long long step, long long n, float* rays_out, float* target_out,
+                                  int* index_out, cudaStream_t stream) {
+    if (n == 0) return 0;
+    if (!K4 || !c2w12 || !rays_out || H <= 0 || W <= 0 || n < 0 || n > (long long)H * W || (long long)H * W >= (1ll << 31) ||
+        (target_out && !image))
+        return -1;
+    const CamParams cp = make_cam(H, W, K4, c2w12, ndc, near, far, K4[0]);
+    const uint32_t n_pix = (uint32_t)((long long)H * W);
+    int half_bits = 1;
+    while ((1ull << (2 * half_bits)) < n_pix) ++half_bits;
+    // key schedule on the host: splitmix64 of (seed, step)
+    unsigned long long zk = seed * 0x9e3779b97f4a7c15ull + step + 0x632be59bd9b4e019ull;
+    zk = (zk ^ (zk >> 30)) * 0xbf58476d1ce4e5b9ull;
+    zk = (zk ^ (zk >> 27)) * 0x94d049bb133111ebull;
+    zk ^= zk >> 31;
+    select_batch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(cp, image, n_pix, half_bits, (uint32_t)zk, (uint32_t)(zk >> 32), n,
+                                                                          rays_out, target_out, index_out);
+    return launch_ok();
+}
+
+// ---------------------------------------------------------------------------------------------
+// render_rays, forward only, as ONE call (run_nerf.py:348-457 with perturb = 0, raw_noise_std = 0: the test-view path):
+// coarse depths -> MLP(coarse) -> composite -> sample_pdf + merge -> MLP(fine) -> composite.
+// ---------------------------------------------------------------------------------------------
+extern "C" int nerfq_mlp_forward(const void* packed, const float* rays, const float* z, long long n_rays, int samples_per_ray, float* raw,
+                                  void* save, int max_ctas, cudaStream_t stream);
+
+extern "C" unsigned long long nerfq_render_rays_workspace_bytes(long long n_rays, int S, int Ni) {
+    if (n_rays <= 0 || S <= 0 || Ni < 0) return 0;
+    // z0 [n,S] | raw0 [n,S,4] | w0 [n,S] | z1 [n,S+Ni] | raw1 [n,S+Ni,4], each rounded up to 256 bytes
+    auto up = [](unsigned long long b) { return (b + 255ull) / 256ull * 256ull; };
+    const unsigned long long n = (unsigned long long)n_rays;
+    return up(4 * n * S) + up(16 * n * S) + up(4 * n * S) + up(4 * n * (S + Ni)) + up(16 * n * (S + Ni));
+}
+
+extern "C" int nerfq_render_rays_fwd(const void* packed_coarse, const void* packed_fine, const float* rays, long long n_rays, int S, int Ni,
+                                      int lindisp, int white_bkgd, void* workspace, float* rgb, float* disp, float* acc, float* rgb0,
+                                      float* disp0, float* acc0, float* z_std, int max_ctas, cudaStream_t stream) {
+    if (n_rays == 0) return 0;
+    if (!packed_coarse || !rays || !workspace || !rgb || !disp || !acc || n_rays < 0 || S < 3 || Ni < 0) return -1;
+    if (Ni > 0 && (!rgb0 || !disp0 || !acc0 || S + Ni > 32 * kMaxPerLane)) return -1;
+    auto up = [](unsigned long long b) { return (b + 255ull) / 256ull * 256ull; };
+    const unsigned long long n = (unsigned long long)n_rays;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    float* z0 = reinterpret_cast<float*>(ws); ws += up(4 * n * S);
+    float* raw0 = reinterpret_cast<float*>(ws); ws += up(16 * n * S);
+    float* w0 = reinterpret_cast<float*>(ws); ws += up(4 * n * S);
+    float* z1 = reinterpret_cast<float*>(ws); ws += up(4 * n * (S + Ni));
+    float* raw1 = reinterpret_cast<float*>(ws);
+    int rc = nerfq_coarse_depths(rays, nullptr, n_rays, S, lindisp, z0, stream);
+    if (rc) return rc;
+    rc = nerfq_mlp_forward(packed_coarse, rays, z0, n_rays, S, raw0, nullptr, max_ctas, stream);
+    if (rc) return rc;
+    if (Ni == 0) return nerfq_composite_fwd(raw0, z0, rays, nullptr, white_bkgd, n_rays, S, rgb, disp, acc, nullptr, nullptr, stream);
+    rc = nerfq_composite_fwd(raw0, z0, rays, nullptr, white_bkgd, n_rays, S, rgb0, disp0, acc0, nullptr, w0, stream);
+    if (rc) return rc;
+    rc = nerfq_sample_fine(z0, nullptr, w0, nullptr, n_rays, S, Ni, z1, z_std, nullptr, stream);
+    if (rc) return rc;
+    rc = nerfq_mlp_forward(packed_fine ? packed_fine : packed_coarse, rays, z1, n_rays, S + Ni, raw1, nullptr, max_ctas, stream);
+    if (rc) return rc;
+    return nerfq_composite_fwd(raw1, z1, rays, nullptr, white_bkgd, n_rays, S + Ni, rgb, disp, acc, nullptr, nullptr, stream);
 }

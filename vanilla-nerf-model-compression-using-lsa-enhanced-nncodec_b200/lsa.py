@@ -83,6 +83,7 @@ class LSAStep:
         self.loss2 = torch.zeros(2, device=dev)
         self.rays = torch.zeros(2, self.n_rays, 3, device=dev)         # [rays_o, rays_d] as run_nerf.py:739 passes batch_rays
         self.target = torch.zeros(self.n_rays, 3, device=dev)
+        self.packed_rays = torch.zeros(self.n_rays, 11, device=dev)    # the iteration's input: rows [o, d, near, far, viewdir]
         self.graph = None
         self.loss = None
 
@@ -114,13 +115,20 @@ class LSAStep:
             return dist.get_world_size(R.DATA_PARALLEL.get("group"))
         return 1
 
-    # the iteration body, eager
-    def step(self, rays: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    def _pack(self, rays: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[2, n, 3] (rays_o, rays_d) -> packed rows [n, 11] (viewdirs, NDC warp, near / far), run_nerf.py:108-142."""
+        focal = float(self.K[0][0]) if self.ndc else 1.0
+        packed_rays = ops.pack_rays(rays[0], rays[1], self.ndc, self.H, self.W, focal, self.near, self.far)
+        if out is not None:
+            out.copy_(packed_rays)
+            return out
+        return packed_rays
+
+    # the iteration body on packed rays
+    def step_packed(self, packed_rays: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         if self.requantize is not None:
             self.requantize()
         kw = self.train_kwargs
-        focal = float(self.K[0][0]) if self.ndc else 1.0
-        packed_rays = ops.pack_rays(rays[0], rays[1], self.ndc, self.H, self.W, focal, self.near, self.far)
         n_norm = self.n_rays * self.world()
         self.loss2.zero_()
         self.grad.zero_()
@@ -137,6 +145,10 @@ class LSAStep:
                     R._backward_pipeline(cfg, st, None, d_rgb, g_out=self.grad)
             self.optimizer.step()
             return self.loss2.sum()
+
+    # the iteration body, eager, from (rays_o, rays_d)
+    def step(self, rays: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        return self.step_packed(self._pack(rays), target)
 
     def _init_optimizer_state(self):
         """Create Adam's state (step, exp_avg, exp_avg_sq) the way torch.optim.Adam does on its first step().  Inside a
@@ -160,11 +172,11 @@ class LSAStep:
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self.step(self.rays, self.target)
+                self.step_packed(self._pack(self.rays, self.packed_rays), self.target)
         torch.cuda.current_stream(self.device).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self.loss = self.step(self.rays, self.target)
+            self.loss = self.step_packed(self.packed_rays, self.target)
         self.graph = graph
         return self
 
@@ -175,6 +187,19 @@ class LSAStep:
             return self.step(rays.to(self.device, non_blocking=True), target.to(self.device, non_blocking=True))
         self.rays.copy_(rays, non_blocking=True)
         self.target.copy_(target, non_blocking=True)
+        self._pack(self.rays, self.packed_rays)
+        self.graph.replay()
+        return self.loss
+
+    def step_selected(self, image: torch.Tensor, H: int, W: int, K, c2w, seed: int, step: int) -> torch.Tensor:
+        """One iteration on a batch chosen ON THE DEVICE (run_nerf.py:690-735 draws np.random.choice(H*W, N_rand) and gathers
+        rays and colours on the host every step): n_rays distinct pixels of `image` [H, W, 3] (device tensor), their rays from
+        the pose `c2w` and their colours, by one kernel (ops.select_batch) straight into the step's input buffers, then the
+        iteration itself (graph replay when captured).  No host random numbers, no host<->device traffic."""
+        ops.select_batch(H, W, K, c2w, image, self.n_rays, seed, step, ndc=self.ndc, near=self.near, far=self.far,
+                         rays_out=self.packed_rays, target_out=self.target)
+        if self.graph is None:
+            return self.step_packed(self.packed_rays, self.target)
         self.graph.replay()
         return self.loss
 

@@ -42,6 +42,13 @@ _PROTOS = {
     "nerfq_mlp_backward_partial": (_c.c_int, [_c.c_void_p] * 4 + [_c.c_longlong, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "nerfq_mlp_backward_finalize": (_c.c_int, [_c.c_void_p] * 4),
     "nerfq_mlp_grad_fix_bytes": (_c.c_ulonglong, []),
+    "nerfq_render_rays_workspace_bytes": (_c.c_ulonglong, [_c.c_longlong, _c.c_int, _c.c_int]),
+    "nerfq_render_rays_fwd": (_c.c_int, [_c.c_void_p] * 3 + [_c.c_longlong, _c.c_int, _c.c_int, _c.c_int, _c.c_int] + [_c.c_void_p] * 8 +
+                              [_c.c_int, _c.c_void_p]),
+    "nerfq_to8b": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_void_p]),
+    "nerfq_select_batch": (_c.c_int, [_c.c_int, _c.c_int, _c.POINTER(_c.c_float), _c.POINTER(_c.c_float), _c.c_int, _c.c_float, _c.c_float,
+                                      _c.c_void_p, _c.c_ulonglong, _c.c_ulonglong, _c.c_longlong, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                      _c.c_void_p]),
 }
 _bound = False
 
@@ -258,3 +265,59 @@ def mlp_backward_finalize(net: PackedNet, grad_fix: torch.Tensor, d_scale: torch
     assert d_scale.is_cuda and d_scale.dtype == torch.float32 and d_scale.is_contiguous() and d_scale.numel() == 2436
     _lib.check(L().nerfq_mlp_backward_finalize(net.ptr, grad_fix.data_ptr(), d_scale.data_ptr(), _stream()), "nerfq_mlp_backward_finalize")
     return d_scale
+
+
+# ---- one-call forward render, image output, batch selection ---------------------------------------------------
+_RENDER_WS = {}
+
+
+def render_rays_fwd(net0: PackedNet, net1: Optional[PackedNet], rays: torch.Tensor, n_samples: int, n_importance: int, lindisp: bool,
+                    white_bkgd: bool, max_ctas: int = 0):
+    """nerfq_render_rays_fwd: (rgb, disp, acc, rgb0, disp0, acc0, z_std) for rays [N,11]; the last four are None when
+    n_importance == 0.  The workspace is kept per (device, size) and reused by later calls on the same stream order."""
+    rays = _f32(rays)
+    n, dev = rays.shape[0], rays.device
+    f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    rgb, disp, acc = f(n, 3), f(n), f(n)
+    rgb0 = disp0 = acc0 = z_std = None
+    if n_importance > 0:
+        rgb0, disp0, acc0, z_std = f(n, 3), f(n), f(n), f(n)
+    if n == 0:
+        return rgb, disp, acc, rgb0, disp0, acc0, z_std
+    need = int(L().nerfq_render_rays_workspace_bytes(n, int(n_samples), int(n_importance)))
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    ws = _RENDER_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _RENDER_WS[key] = torch.empty(need, dtype=torch.uint8, device=dev)
+    _lib.check(L().nerfq_render_rays_fwd(net0.ptr, net1.ptr if net1 is not None else None, rays.data_ptr(), n, int(n_samples), int(n_importance),
+                                         int(lindisp), int(white_bkgd), ws.data_ptr(), rgb.data_ptr(), disp.data_ptr(), acc.data_ptr(),
+                                         _p(rgb0), _p(disp0), _p(acc0), _p(z_std), max_ctas, _stream()), "nerfq_render_rays_fwd")
+    return rgb, disp, acc, rgb0, disp0, acc0, z_std
+
+
+def to8b(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(255 * clip(x, 0, 1)).astype(uint8) on the device (run_nerf_helpers.py:14)."""
+    x = _f32(x)
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() == x.numel()
+    _lib.check(L().nerfq_to8b(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "nerfq_to8b")
+    return out
+
+
+def select_batch(H: int, W: int, K, c2w, image: Optional[torch.Tensor], n: int, seed: int, step: int, ndc: bool = False, near: float = 0.,
+                 far: float = 1., device=None, want_index: bool = False, rays_out: Optional[torch.Tensor] = None,
+                 target_out: Optional[torch.Tensor] = None):
+    """n distinct pixels of an image: (packed rays [n,11], target colours [n,3] | None, pixel indices | None)."""
+    dev = image.device if image is not None else device
+    k4 = (_c.c_float * 4)(float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]))
+    c12 = (_c.c_float * 12)(*[float(c2w[r][col]) for r in range(3) for col in range(4)])
+    rays = rays_out if rays_out is not None else torch.empty((n, 11), dtype=torch.float32, device=dev)
+    target = None
+    if image is not None:
+        image = _f32(image.reshape(-1, 3), H * W, 3)
+        target = target_out if target_out is not None else torch.empty((n, 3), dtype=torch.float32, device=dev)
+    idx = torch.empty((n,), dtype=torch.int32, device=dev) if want_index else None
+    _lib.check(L().nerfq_select_batch(int(H), int(W), k4, c12, int(ndc), float(near), float(far), _p(image), int(seed) & (2 ** 64 - 1),
+                                      int(step) & (2 ** 64 - 1), int(n), rays.data_ptr(), _p(target), _p(idx), _stream()), "nerfq_select_batch")
+    return rays, target, idx

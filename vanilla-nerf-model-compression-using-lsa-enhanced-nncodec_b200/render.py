@@ -287,6 +287,19 @@ def render_rays(ray_batch, network_fn, network_query_fn=None, N_samples=64, retr
     need_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (sc0, sc1))
     if need_grad:
         outs = _RenderRaysFn.apply(cfg, sc0, sc1)
+    elif not retraw and cfg.t_rand is None and cfg.u is None and cfg.noise0 is None and cfg.noise1 is None:
+        # the test-view path (perturb = 0, raw_noise_std = 0): the whole of render_rays is one C-ABI call
+        with torch.no_grad():
+            pn0 = _refresh(network_fn, sc0)
+            pn1 = None
+            if cfg.Ni > 0 and network_fine is not None:
+                pn1 = _refresh(network_fine, sc1)
+            rgb, disp, acc, rgb0, disp0, acc0, z_std = ops.render_rays_fwd(pn0, pn1, rays, cfg.S, cfg.Ni, cfg.lindisp, cfg.white,
+                                                                           max_ctas=TUNING["max_ctas"])
+        ret = {"rgb_map": rgb, "disp_map": disp, "acc_map": acc}
+        if cfg.Ni > 0:
+            ret.update(rgb0=rgb0, disp0=disp0, acc0=acc0, z_std=z_std)
+        return ret
     else:
         with torch.no_grad():
             outs, _ = _forward_pipeline(cfg, sc0, sc1, save=False)
@@ -339,24 +352,110 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
     return [all_ret[k] for k in k_extract] + [{k: v for k, v in all_ret.items() if k not in k_extract}]
 
 
+class _FrameRing:
+    """Pinned host buffers + a copy stream: frame i's device->host copy runs while frame i+1 renders (the reference's
+    render_path does `rgb.cpu().numpy()` per view, a synchronous pageable copy, run_nerf.py:196-199)."""
+
+    def __init__(self, dev, shapes_dtypes, depth=2):
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.slots = [[torch.empty(sh, dtype=dt).pin_memory() for sh, dt in shapes_dtypes] for _ in range(depth)]
+        self.events = [None] * depth
+        self.dev = dev
+        self.i = 0
+
+    def push(self, tensors):
+        """Start copying `tensors` (device) into the next slot; returns (slot index, the slot's host tensors)."""
+        k = self.i % len(self.slots)
+        self.i += 1
+        if self.events[k] is not None:
+            self.events[k].synchronize()                     # the slot's previous frame has been consumed by the caller by now
+        main = torch.cuda.current_stream(self.dev)
+        self.copy_stream.wait_stream(main)
+        with torch.cuda.stream(self.copy_stream):
+            for h, t in zip(self.slots[k], tensors):
+                h.copy_(t, non_blocking=True)
+                t.record_stream(self.copy_stream)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self.events[k] = ev
+        return k, self.slots[k]
+
+    def wait(self, k):
+        self.events[k].synchronize()
+
+
 def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0):
-    """run_nerf.py:161-211 (PNG writing needs imageio and is skipped when it is absent)."""
+    """run_nerf.py:161-211: returns (rgbs [V,H,W,3], disps [V,H,W]) as float32 numpy arrays; with `savedir` every view is
+    also written as 8-bit (PNG through imageio when it is installed, else .npy).  The 8-bit conversion (to8b) runs on the
+    device and all device->host copies are asynchronous, double-buffered through pinned memory, so the copy and the file
+    write of view i overlap the rendering of view i+1."""
     H, W, focal = hwf
     if render_factor != 0:
         H, W, focal = H // render_factor, W // render_factor, focal / render_factor
-    rgbs, disps = [], []
+    n_views = len(render_poses)
+    rgbs = np.empty((n_views, H, W, 3), dtype=np.float32)
+    disps = np.empty((n_views, H, W), dtype=np.float32)
+    if n_views == 0:
+        return rgbs, disps
+    dev = torch.device("cuda", torch.cuda.current_device())
+    shapes = [((H, W, 3), torch.float32), ((H, W), torch.float32)] + ([((H, W, 3), torch.uint8)] if savedir is not None else [])
+    ring = _FrameRing(dev, shapes)
+    writer = None
+    if savedir is not None:
+        try:
+            import imageio
+            writer = lambda i, img: imageio.imwrite(os.path.join(savedir, "{:03d}.png".format(i)), img)
+        except ImportError:
+            writer = lambda i, img: np.save(os.path.join(savedir, "{:03d}.npy".format(i)), img)
+
+    def drain(i, k, host):
+        ring.wait(k)
+        rgbs[i] = host[0].numpy()
+        disps[i] = host[1].numpy()
+        if writer is not None:
+            writer(i, host[2].numpy())
+
+    pending = None
     for i, c2w in enumerate(render_poses):
         with torch.no_grad():
             rgb, disp, acc, _ = render(H, W, K, chunk=chunk, c2w=c2w[:3, :4], **render_kwargs)
-        rgbs.append(rgb.cpu().numpy())
-        disps.append(disp.cpu().numpy())
-        if savedir is not None:
-            try:
-                import imageio
-                imageio.imwrite(os.path.join(savedir, "{:03d}.png".format(i)), to8b(rgbs[-1]))
-            except ImportError:
-                np.save(os.path.join(savedir, "{:03d}.npy".format(i)), to8b(rgbs[-1]))
-    return np.stack(rgbs, 0), np.stack(disps, 0)
+            frame = [rgb, disp] + ([ops.to8b(rgb)] if savedir is not None else [])
+        k, host = ring.push(frame)
+        if pending is not None:
+            drain(*pending)                                   # view i-1 lands while view i renders
+        pending = (i, k, host)
+    drain(*pending)
+    return rgbs, disps
+
+
+def render_path_8bit(render_poses, hwf, K, chunk, render_kwargs, sink=None, first_view=0, view_count=None, render_factor=0):
+    """The image-output leg of run_nerf.py:196-211 alone, for test-set sweeps: every view is rendered, converted to 8 bit on the
+    device (to8b, run_nerf_helpers.py:14) and copied out asynchronously (3 bytes per pixel instead of 16); `sink(i, uint8[H,W,3])`
+    is called once the frame is on the host while the next view renders.  Views [first_view, first_view + view_count) only --
+    the view-major shard of one rank (distributed.shard_range).  Returns the number of views rendered."""
+    H, W, focal = hwf
+    if render_factor != 0:
+        H, W, focal = H // render_factor, W // render_factor, focal / render_factor
+    last = len(render_poses) if view_count is None else first_view + view_count
+    if last <= first_view:
+        return 0
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ring = _FrameRing(dev, [((H, W, 3), torch.uint8)])
+    pending = None
+    for i in range(first_view, last):
+        with torch.no_grad():
+            rgb, _, _, _ = render(H, W, K, chunk=chunk, c2w=render_poses[i][:3, :4], **render_kwargs)
+            img = ops.to8b(rgb)
+        k, host = ring.push([img])
+        if pending is not None:
+            ring.wait(pending[1])
+            if sink is not None:
+                sink(pending[0], pending[2][0].numpy())
+        pending = (i, k, host)
+    ring.wait(pending[1])
+    if sink is not None:
+        sink(pending[0], pending[2][0].numpy())
+    return last - first_view
 
 
 def create_nerf(nerf_wrapper, multires=10, i_embed=0, use_viewdirs=True, multires_views=4, netchunk=1024 * 64, basedir=None,
