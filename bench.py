@@ -8,7 +8,12 @@
 One "step" is BASELINE configs[1]: an LSA fine-tuning step at qp=-20 on a 4096-ray batch per GPU
 (quantise -> on-the-fly LSA-scaled dequantisation -> render 64+128 -> backward into the LSA scales -> Adam),
 synthetic rays and a random-init vanilla NeRF.  Multi-GPU runs are data parallel (weak scaling: 4096 rays per
-GPU, one 19.5 KB NCCL all-reduce of the scale gradients per step).  Prints ONE JSON line on rank 0.
+GPU, two 19.5 KB NCCL all-reduces of the fixed-point scale-gradient sums per step).  Prints ONE JSON line on rank 0.
+
+Other BASELINE configs as extra modes (same JSON contract, one line each; not run by the driver):
+    --mode cfg3    one 800x800 blender-shaped test view, pixels sharded contiguously over the ranks
+    --mode cfg4    120 LLFF-shaped 378x504 NDC views, view-major over the ranks, 8-bit images copied out asynchronously
+    --mode cfg5    data-parallel LSA steps with a qp sweep -38..-10 (levels of every tensor checked against the host coder)
 """
 import argparse
 import json
@@ -154,13 +159,21 @@ def cpu_lsa_steps(p, n_rays, steps, warmup, seed=2, device=None):
 
 
 def run_reference(args):
+    """The reference algorithm (oracle port, pinned to the unmodified reference by tests/golden) on the host cores: WHOLE
+    4096-ray LSA steps, all threads.  One step takes ~3-4 s on a 16-24 core box; if the first step shows that
+    steps+warmup would not fit ~5 minutes, the remaining steps use a 1024-ray sample and the line says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    sample = 512
     p = oracle_model()
-    sec, threads = cpu_lsa_steps(p, sample, args.steps, max(args.warmup, 1))
+    t0 = time.perf_counter()
+    sec1, threads = cpu_lsa_steps(p, RAYS_PER_GPU, 1, 0)
+    budget = 300.0 - (time.perf_counter() - t0)
+    sample = RAYS_PER_GPU
+    if sec1 * (args.steps + max(args.warmup - 1, 0)) > budget:
+        sample = 1024
+    sec, threads = cpu_lsa_steps(p, sample, args.steps, max(args.warmup - 1, 0) if sample == RAYS_PER_GPU else 1)
     rays_s = sample / sec
     line = {"metric": METRIC, "value": rays_s, "unit": "rays/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3 * RAYS_PER_GPU / sample, "higher_is_better": True, "scaling": "weak",
@@ -168,7 +181,7 @@ def run_reference(args):
             "lsa_steps_per_sec": rays_s / RAYS_PER_GPU,
             "config": {"workload": WORKLOAD, "rays_per_gpu": RAYS_PER_GPU, "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE, "qp": QP,
                        "perturb": 1.0, "white_bkgd": True, "implementation": "CPU oracle port of the reference (stock torch fp32)",
-                       "rays_per_step_sample": sample},
+                       "rays_per_step_timed": sample, "whole_steps": sample == RAYS_PER_GPU},
             "cpu_baseline": {"value": rays_s, "unit": "rays/s", "cores": threads, "kind": "port",
                              "sample": f"{sample}-ray LSA steps (fwd+bwd+Adam), torch CPU fp32, mean of {args.steps}"},
             "e2e": {"value": rays_s, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -300,6 +313,12 @@ def run_cuda(args):
                                               if world == 1 else None, RAYS_PER_GPU * S * FLOP_PER_POINT_FWD)
             del save
 
+    # (5) data parallel only: the exposed cost of the gradient all-reduces (same captured step with the collective switched
+    # off) and the bit-parity of the data-parallel gradients against ONE rank stepping on the concatenated global batch
+    dp_info = None
+    if world > 1:
+        dp_info = dp_checks(dev, rank, world, timed, rays_d, t_d, step_kw)
+
     if rank == 0:
         pk = peaks()
         rays_s = world * RAYS_PER_GPU / (ms_step * 1e-3)
@@ -323,8 +342,19 @@ def run_cuda(args):
         # coarse_depths 1, sample_fine 1, mse_grad 0 (torch), bwd: 2 x (composite_bwd 1 + mlp_bwd 1 + finalize 1);
         # requantise: absmax + quantize (batched over the 48 tensors) + 2 nets x (2 pack kernels + set_scale_bias);
         # matches the ncu launch list (profiles/r01_launches_lsa_step_summary.txt: 23 of the 54 launches are nerfq kernels)
-        per_step = 1 + 2 * 3 + 1 + 1 + 2 * 3 + (2 + 6 if requant_each_step else 0)
+        per_step = 1 + 2 * 3 + 1 + 1 + 1 + 2 * 3 + (2 + 6 if requant_each_step else 0)
         line["gpu_launches"] = per_step * args.steps
+        fwd_rays_s = world * n_view / (ms_view * 1e-3)
+        line["forward"] = {"metric": "rays/sec render_rays forward only (test-view path, 64+128 samples/ray, chunk 32768)",
+                           "value": fwd_rays_s, "unit": "rays/s", "rays_per_call_per_gpu": n_view,
+                           "view_800x800_ms": ms_cfg3, "view_800x800_rays_per_sec": H * W / (ms_cfg3 * 1e-3),
+                           "roofline": {"bound": "tensor", "achieved": fwd_rays_s / world * 256 * FLOP_PER_POINT_FWD / 1e12,
+                                        "peak": pk["tensor"], "unit": "TFLOP/s",
+                                        "frac": fwd_rays_s / world * 256 * FLOP_PER_POINT_FWD / 1e12 / pk["tensor"],
+                                        "peak_source": pk["source"] + " (sustained bf16: whole render calls, all kernels included)"}}
+        if dp_info is not None:
+            line["dp_parity"] = dp_info["parity"]
+            line["allreduce"] = dp_info["allreduce"]
         if world == 1:
             rows = {k: {"ms": v[0], "tflops": v[1] / (v[0] * 1e-3) / 1e12} for k, v in kern.items()}
             step_kernel_ms = sum(rows[k]["ms"] for k in ("mlp_fwd_coarse", "mlp_fwd_fine", "mlp_bwd_coarse", "mlp_bwd_fine"))
@@ -376,17 +406,279 @@ def run_cuda(args):
         os._exit(0)
 
 
+def _dist_setup():
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the nerfq kernels)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    return rank, world, local, dev
+
+
+def _timed_region(world, dev, fn, steps, warmup):
+    """W warm-up calls, then `steps` calls between barrier + synchronize, CUDA events, max over ranks -> ms per call."""
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()) / steps
+
+
+def _finish(world):
+    import torch.distributed as dist
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
+def llff_spiral_poses(n_views=120):
+    """A synthetic forward-facing spiral in the shape of load_llff.py:151-160 / 287-298 (render_path_spiral with rots=2,
+    zrate=.5 around an identity average pose): [n_views, 3, 4] camera-to-world matrices."""
+    def normalize(x):
+        return x / np.linalg.norm(x)
+    up, focal, rads = np.array([0.0, 1.0, 0.0]), 3.0, np.array([0.4, 0.3, 0.1, 1.0])
+    c2w = np.concatenate([np.eye(3), np.zeros((3, 1))], 1)
+    poses = []
+    for theta in np.linspace(0.0, 2.0 * np.pi * 2, n_views + 1)[:-1]:
+        c = c2w @ (np.array([np.cos(theta), -np.sin(theta), -np.sin(theta * 0.5), 1.0]) * rads)
+        zv = normalize(c - c2w @ np.array([0.0, 0.0, -focal, 1.0]))
+        xv = normalize(np.cross(up, zv))
+        yv = normalize(np.cross(zv, xv))
+        poses.append(np.stack([xv, yv, zv, c], 1).astype(np.float32))
+    return np.stack(poses, 0)
+
+
+def run_views(args):
+    """--mode cfg3 / cfg4: test-view rendering (forward only) sharded over the ranks, no data-path collective.
+    cfg3: ONE 800x800 blender-shaped view per step, pixels split contiguously over the ranks (strong scaling).
+    cfg4: the 120-view LLFF-shaped set (378x504, NDC, near 0, far 1) per step, view-major over the ranks (strong scaling);
+          e2e = render_path_8bit: to8b on the device + asynchronous double-buffered copy of every 8-bit frame to pinned host memory."""
+    rank, world, local, dev = _dist_setup()
+    import nerfq_b200  # noqa: F401
+    from nerfq_b200 import codec, distributed as D, model as nmodel, ops, render as R
+    torch.manual_seed(0)
+    wrapper = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params().to(dev)
+    codec.quantize_model(wrapper, QP, QP_DENSITY, NONWEIGHT_QP)
+    cfg4 = args.mode == "cfg4"
+    sampler = ClockSampler(local)
+    if cfg4:
+        H, W, focal, n_views = 378, 504, 407.5658, 120
+        K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]], dtype=np.float32)
+        _, kw = R.create_nerf(wrapper, white_bkgd=False, dataset_type="llff", N_importance=N_IMPORTANCE)
+        kw = dict(kw, near=0.0, far=1.0)
+        poses = [torch.from_numpy(p) for p in llff_spiral_poses(n_views)]
+        first, count = D.shard_range(n_views, rank, world)
+        view_kw = {k: v for k, v in kw.items() if k not in ("use_viewdirs", "network_query_fn", "ndc", "near", "far")}
+
+        def device_only():
+            with torch.no_grad():
+                for i in range(first, first + count):
+                    rays = ops.camera_rays(H, W, K, poses[i].numpy(), True, 0.0, 1.0, dev)
+                    R.batchify_rays(rays, 32768, **view_kw)
+        got = []
+
+        def e2e():
+            got.clear()
+            R.render_path_8bit(poses, (H, W, focal), K, 32768, kw, sink=lambda i, im: got.append(int(im[0, 0, 0])), first_view=first, view_count=count)
+        total_rays = n_views * H * W
+        workload = "cfg4: 120 LLFF-fern-shaped 378x504 NDC views (near 0, far 1, 64+128 samples), view-major over the ranks, random-init vanilla NeRF at qp -20"
+        d2h = count * H * W * 3
+        steps, warmup = max(1, min(args.steps, 3)), 1
+    else:
+        H = W = 800
+        f_cam = 0.5 * W / np.tan(0.5 * 0.6911112070083618)
+        K = np.array([[f_cam, 0, 0.5 * W], [0, f_cam, 0.5 * H], [0, 0, 1]], dtype=np.float32)
+        c2w = np.array([[1, 0, 0, 0.0], [0, 0.8660254, 0.5, 2.0], [0, -0.5, 0.8660254, 3.4641016]], dtype=np.float32)
+        _, kw = R.create_nerf(wrapper, white_bkgd=True, dataset_type="blender")
+        first, count = D.shard_range(H * W, rank, world)
+        view_kw = {k: v for k, v in kw.items() if k not in ("use_viewdirs", "network_query_fn", "ndc", "near", "far")}
+        host = torch.empty((count, 3), dtype=torch.uint8).pin_memory()
+
+        def device_only():
+            with torch.no_grad():
+                rays = ops.camera_rays(H, W, K, c2w, False, 2.0, 6.0, dev, first_pixel=first, count=count)
+                return R.batchify_rays(rays, 32768, **view_kw)
+
+        def e2e():
+            ret = device_only()
+            host.copy_(ops.to8b(ret["rgb_map"]), non_blocking=True)
+            torch.cuda.synchronize()
+        total_rays = H * W
+        workload = "cfg3: one 800x800 blender-lego-shaped test view (64+128 samples), pixels sharded contiguously over the ranks, random-init vanilla NeRF at qp -20"
+        d2h = count * 3
+        steps, warmup = max(3, min(args.steps, 10)), 3
+    if rank == 0:
+        sampler.start()
+    ms = _timed_region(world, dev, device_only, steps, warmup)
+    ms_e2e = _timed_region(world, dev, e2e, steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        pk = peaks()
+        rays_s = total_rays / (ms * 1e-3)
+        tf = rays_s / world * 256 * FLOP_PER_POINT_FWD / 1e12
+        chunks = count * ((H * W + 32767) // 32768) if cfg4 else (count + 32767) // 32768
+        line = {"metric": METRIC, "value": rays_s, "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                "config": {"workload": workload, "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE, "qp": QP, "chunk": 32768,
+                           "operands": "fp16 operands, fp32 accumulate (TMEM)", "parallelism": f"rays sharded over {world} rank(s), no collective",
+                           "l2": "every chunk streams 137 MB of intermediates (> 126 MB L2); no explicit flush"},
+                "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": int(d2h), "note": "poses are 48-byte kernel arguments; the result copied out is the 8-bit image"},
+                "roofline": {"bound": "tensor", "kernel": "mlp3_forward_kernel (whole render calls timed)", "achieved": tf, "peak": pk["tensor"],
+                             "unit": "TFLOP/s", "frac": tf / pk["tensor"], "traffic": None, "peak_source": pk["source"] + " (sustained bf16)"},
+                "gpu_launches": int(steps * chunks * 6 + steps * (count if cfg4 else 1)), "clocks": clocks}
+        print(json.dumps(line))
+    _finish(world)
+
+
+def run_qp_sweep(args):
+    """--mode cfg5: data-parallel LSA tuning (4096 rays per rank) at every qp of -38..-10.  Per qp: the levels of all 48
+    weight / bias tensors from the GPU quantiser are compared with the host coder's uniform quantiser (libnncabac.so, the
+    module that entropy-codes them) -- bit-exact or the run fails -- then `steps` captured LSA steps are timed."""
+    rank, world, local, dev = _dist_setup()
+    import nerfq_b200  # noqa: F401
+    from nerfq_b200 import codec, deepcabac, distributed as D, lsa, model as nmodel
+    torch.manual_seed(0)
+    wrapper = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params().to(dev)
+    master = {k: v.detach().clone() for k, v in wrapper.state_dict().items()}
+    master_host = {k: np.ascontiguousarray(v.cpu().numpy()) for k, v in master.items()}
+    D.enable_data_parallel(world > 1)
+    o_h, d_h, t_h = synth_batch(RAYS_PER_GPU, 2 + 10 * rank)
+    rays_d, t_d = torch.stack([o_h, d_h], 0).to(dev), t_h.to(dev)
+    names = ["pts_linears.%d" % i for i in range(8)] + ["alpha_linear", "feature_linear", "views_linears.0", "rgb_linear"]
+    per_qp, all_ok = {}, True
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    steps = max(3, min(args.steps, 10))
+    for qp in range(-38, -9):
+        wrapper.load_state_dict(master)
+        lv = codec.quantize_model(wrapper, qp, QP_DENSITY, NONWEIGHT_QP)
+        ok = True
+        if rank == 0:
+            for net in ("model", "model_fine"):
+                for i, l in enumerate(names):
+                    for kind, q in (("weight", qp), ("bias", NONWEIGHT_QP)):
+                        host, used = deepcabac.host_quant_layer(master_host[f"{net}.{l}.{kind}"], 0, QP_DENSITY, q)
+                        ok = ok and used == q and bool((lv[net][f"{i}.{kind}"].cpu().numpy() == host).all())
+        step = lsa.LSAStep(wrapper, RAYS_PER_GPU, requantize=None, lr=1e-4, perturb=1.0, white_bkgd=True, dataset_type="blender")
+        step.capture()
+        ms = _timed_region(world, dev, lambda: step(rays_d, t_d), steps, 3)
+        step.graph = None
+        per_qp[qp] = {"ms_per_step": ms, "levels_bit_exact_vs_host_coder": ok}
+        all_ok = all_ok and ok
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        ms_mean = float(np.mean([v["ms_per_step"] for v in per_qp.values()]))
+        line = {"metric": METRIC, "value": world * RAYS_PER_GPU / (ms_mean * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": 3,
+                "ms_per_step": ms_mean, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                "lsa_steps_per_sec": 1e3 / ms_mean,
+                "config": {"workload": f"cfg5: data-parallel LSA steps ({world} x 4096 rays/step), qp sweep -38..-10, levels checked per qp",
+                           "parallelism": f"dp{world}", "qps": list(per_qp.keys())},
+                "levels_bit_exact_every_qp": all_ok, "per_qp": {str(k): v for k, v in per_qp.items()}, "clocks": clocks,
+                "gpu_launches": int(steps * 29 * 17)}
+        print(json.dumps(line))
+        if not all_ok:
+            sys.stderr.write("cfg5: quantised levels differ from the host coder\n")
+    _finish(world)
+
+
+def dp_checks(dev, rank, world, timed, rays_d, t_d, step_kw):
+    """Rank-collective: (a) the same captured LSA step with and without the gradient all-reduces -> exposed collective time;
+    (b) the all-reduce alone; (c) gradients / updated scales of `world` ranks x 1024 rays == one rank x (world*1024) rays."""
+    import torch.distributed as dist
+    from nerfq_b200 import codec, distributed as D, lsa, model as nmodel, render as R
+
+    def make():
+        torch.manual_seed(0)
+        w = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params().to(dev)
+        codec.quantize_model(w, QP)
+        return w
+    out = {}
+    # (a) exposed time
+    res = {}
+    for dp in (True, False):
+        D.enable_data_parallel(dp)
+        st = lsa.LSAStep(make(), RAYS_PER_GPU, requantize=None, **step_kw)
+        st.capture()
+        res[dp] = timed(lambda: st(rays_d, t_d), 20, 5)
+        st.graph = None
+    # (b) the collective alone: two int64[2440] all-reduces back to back (what a step issues)
+    D.enable_data_parallel(True)
+    fix = torch.zeros((2, 2440), dtype=torch.int64, device=dev)
+
+    def ar():
+        dist.all_reduce(fix[1])
+        dist.all_reduce(fix[0])
+    ms_ar = timed(ar, 50, 10)
+    out["allreduce"] = {"ms_step_with": res[True], "ms_step_without": res[False], "ms_exposed": res[True] - res[False],
+                        "ms_two_allreduces_alone": ms_ar, "bytes": 2 * 2440 * 8,
+                        "note": "fine network's all-reduce runs on a side stream under the coarse backward; the coarse one is exposed"}
+    # (c) bit parity
+    n = 1024
+    batches = [synth_batch(n, 2 + 10 * r) for r in range(world)]
+    kw = dict(lr=1e-3, perturb=0.0, white_bkgd=True)
+    D.enable_data_parallel(True)
+    st = lsa.LSAStep(make(), n, **kw)
+    o, d, t = batches[rank]
+    st(torch.stack([o, d]).to(dev), t.to(dev))
+    g_dp, p_dp = st.grad.clone(), st.flat.clone()
+    D.enable_data_parallel(False)
+    st1 = lsa.LSAStep(make(), n * world, **kw)
+    o = torch.cat([b[0] for b in batches]); d = torch.cat([b[1] for b in batches]); t = torch.cat([b[2] for b in batches])
+    st1(torch.stack([o, d]).to(dev), t.to(dev))
+    torch.cuda.synchronize()
+    ok = torch.tensor([int(torch.equal(g_dp, st1.grad)), int(torch.equal(p_dp, st1.flat))], device=dev)
+    gl = [torch.empty_like(g_dp) for _ in range(world)]
+    dist.all_gather(gl, g_dp)
+    same = all(torch.equal(gl[0], x) for x in gl)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    out["parity"] = {"grads_bitwise_equal_to_single_gpu_global_batch": bool(ok[0].item()), "scales_after_adam_bitwise_equal": bool(ok[1].item()),
+                     "grads_equal_across_ranks": bool(same), "rays": f"{world} ranks x {n} vs 1 rank x {n * world}",
+                     "max_abs_grad": float(g_dp.abs().max())}
+    D.enable_data_parallel(True)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--mode", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"], help="BASELINE config to run (default: the headline LSA step)")
     ap.add_argument("--no-requant", action="store_true", help="quantise once before the loop (what the reference does)")
     ap.add_argument("--eager", action="store_true", help="do not capture the LSA iteration in a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode in ("cfg3", "cfg4"):
+        run_views(args)
+    elif args.mode == "cfg5":
+        run_qp_sweep(args)
     else:
         run_cuda(args)
 

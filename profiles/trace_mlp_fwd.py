@@ -30,7 +30,9 @@ buf = torch.zeros(148 * 8 + 148 * 32, dtype=torch.int64, device=dev)
 save = torch.empty(packed.mlp_save_bytes(n * S), dtype=torch.uint8, device=dev)
 for mode, kw, flags in ([("nosave", {}, 0), ("save", {"save": save}, 0)] +
                         [(f"nosave, job {j} timed", {}, j << 8) for j in (0, 1, 2, 3, 8, 9, 14, 15, 18, 19)] +
-                        [(f"nosave, none of the three, job {j} timed", {}, 7 | (j << 8)) for j in (2, 3)]):
+                        [(f"nosave, ablation {name} (flags {fl}), job 2 timed", {}, fl | (2 << 8)) for name, fl in
+                         (("no TMEM loads", 1), ("no operand stores", 2), ("no math", 4), ("no async-proxy fence", 8), ("no alpha head", 16),
+                          ("no encodings", 32), ("no loads/stores/math", 7), ("nothing but the barriers", 63))]):
     for _ in range(2):
         packed.mlp_forward(pn, rays, z, **kw)
     L.nerfq_mlp_set_trace(buf.data_ptr(), flags)

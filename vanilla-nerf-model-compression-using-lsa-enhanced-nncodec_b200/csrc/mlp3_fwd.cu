@@ -41,7 +41,9 @@ struct Fwd3Params {
     int samples_per_ray;
     int n_groups;
     unsigned long long* dbg;     // tracing build only: 8 cycle counters per CTA
-    int dbg_flags;               // tracing build only: 1 skip TMEM loads, 2 skip operand stores, 4 skip conversion math
+    int dbg_flags;               // tracing build only, ablations (results are then wrong, only the timing is of interest):
+                                 // 1 skip TMEM loads, 2 skip operand stores, 4 skip conversion math, 8 publish without the
+                                 // async-proxy fence, 16 skip the alpha-head reduction, 32 skip the encodings; bits 8.. = timed job
     Prog3Fwd prog;
 };
 
@@ -87,9 +89,11 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
         unsigned long long t_acc = 0, t_sf = 0, t_job = 0, t_math = 0, t_sel = 0, t_sel_math = 0;
         const int j_sel = prm.dbg_flags >> 8;
         const bool tracing = kTrace && e == 5 && lane == 0;
+        const bool ab_ld = kTrace && (prm.dbg_flags & 1), ab_st = kTrace && (prm.dbg_flags & 2), ab_math = kTrace && (prm.dbg_flags & 4);
+        const bool ab_fence = kTrace && (prm.dbg_flags & 8), ab_alpha = kTrace && (prm.dbg_flags & 16), ab_pe = kTrace && (prm.dbg_flags & 32);
 
         auto publish = [&](int which) {
-            fence_proxy_async_smem();
+            if (!ab_fence) fence_proxy_async_smem();
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(which));
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                 }
 
                 if (f & JB_DIR_BEFORE) {        // gamma(x) is dead once L5 has been accumulated
-                    if (role == 0) write_dir_enc(enc, pt, vd);
+                    if (role == 0 && !ab_pe) write_dir_enc(enc, pt, vd);
                 }
                 // ---- 4 chunks of 16 points: TMEM -> y = acc*es + b -> (ReLU) -> fp16 -> operand tile ----
                 // The load of chunk i+1 is in flight while chunk i is converted and stored.
@@ -193,7 +197,10 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                     uint32_t pk[8];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) y[i] = fmaf(__uint_as_float(v[i]), c.x, c.y);
-                    if (relu) {
+                    if (ab_math) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) pk[i] = v[2 * i] ^ v[2 * i + 1];
+                    } else if (relu) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) pk[i] = cvt_pack_f16_relu(y[2 * i], y[2 * i + 1]);
                     } else {
@@ -210,12 +217,14 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                             if (tracing) t_sf += clock64() - t1;
                         }
                     }
+                    if (!ab_st) {
 #pragma unroll
-                    for (int k = 0; k < 2; ++k)
-                        st_shared_v4(row_addr + ((uint32_t)((cc * 2 + k) << 4) ^ swz), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+                        for (int k = 0; k < 2; ++k)
+                            st_shared_v4(row_addr + ((uint32_t)((cc * 2 + k) << 4) ^ swz), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+                    }
                     // the same 16 values go to the saved-activation slot: the warp's 32 channels are adjacent, 1 KB per store
                     if (kSave && cc < kSaveInJob) st_global_v8(save_ch + save3_offset(pq * 4 + cc, 0), pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
-                    if (f & JB_ALPHA) {
+                    if ((f & JB_ALPHA) && !ab_alpha) {
                         // Alpha head over this warp's 32 channels (L7 is a ReLU layer: the head sees max(y, 0)), in fixed
                         // point: each term  max(y,0) * level * (delta*scale) of the sigma logit is rounded to 2^-18, the
                         // warp sum is one REDUX per point, and the eight partial sums of a point (4 warps x 2 halves) meet
@@ -237,7 +246,14 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                         if (lane < 16) red_shared_add_s32(out_sa + 4 * (pq * 64 + cc * 16 + lane), mine);
                     }
                 };
-                {
+                if (ab_ld) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) va[i] = vb[i] = (uint32_t)(i + j);
+                    process(va, 0);
+                    process(vb, 1);
+                    process(va, 2);
+                    process(vb, 3);
+                } else {
                     tmem_ld16(ta, va);
                     tmem_ld_wait();
                     tmem_ld16(ta + 16, vb);
@@ -254,7 +270,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                 if (tracing) { const unsigned long long dt = clock64() - t0; t_math += dt; if (j == j_sel) t_sel_math += dt; }
                 if (f & JB_PE_AFTER) {          // the direction stage of this group has been accumulated
                     if (g + stride < prm.n_groups) {
-                        write_pe_half(enc, pt, role, p);
+                        if (!ab_pe) write_pe_half(enc, pt, role, p);
 #pragma unroll
                         for (int k = 0; k < 3; ++k) vd[k] = vd_next[k];
                     }
