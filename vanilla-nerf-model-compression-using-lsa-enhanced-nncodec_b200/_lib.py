@@ -4,7 +4,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnerfq.so")
+# NERFQ_LIB: developer aid for A/B timing of two builds of the same sources on one box (profiles/ab_build.py)
+LIB_PATH = os.environ.get("NERFQ_LIB") or os.path.join(_HERE, "libnerfq.so")
 
 c_void_p, c_int, c_ll, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
 c_ull = ctypes.c_ulonglong

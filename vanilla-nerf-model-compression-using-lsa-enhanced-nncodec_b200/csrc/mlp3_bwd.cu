@@ -241,6 +241,13 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
 
             // ---- views-layer job: d hv[k][n] = sum_c g_c[n] * w_rgb[c][k], channels 0..127 ----
             if (tracing) { const unsigned long long t = clock64(); t_pro += t - tp0; tp0 = t; }
+            H32 hh[2];             // saved activations of the dgrad chain's current job, chunks 0 and 1 (see the job loop)
+            {
+                const Job3 j0 = prm.prog.job[0];
+                const uint8_t* hrow0 = saved_row(g, j0.slot, ((j0.flags & JB_HI_HALF) ? 128u : 0u) + cl);
+                hh[0] = ldg_nc_32B(hrow0 + pair_off(0, 0));
+                hh[1] = ldg_nc_32B(hrow0 + pair_off(1, 0));
+            }
             {
                 const uint32_t chh = cl;                                   // views hidden channel
                 const float2 c = __ldg(&g_sb[kChViews + chh]);
@@ -281,11 +288,12 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 const uint8_t* hrow = saved_row(gj, jb.slot, chh);
                 const uint32_t row_addr = act + (chh >> 3) * kKGroup3 + pq * kNGroup3 + (chh & 7u) * 128u;
                 const uint32_t swz = (chh & 7u) << 4;
-                // saved activations: two chunks are requested before the accumulator is waited for, then each consumed
-                // slot is refilled with the chunk two ahead
-                H32 hh[2];
-                hh[0] = ldg_nc_32B(hrow + pair_off(0, swz));
-                hh[1] = ldg_nc_32B(hrow + pair_off(1, swz));
+                // Saved activations: hh[] holds chunks 0 and 1 of THIS job, requested while the previous job (or the views job)
+                // was still running -- the accumulator of a "hi" job is ready long before its job starts, so loads issued at
+                // the job's start had their whole HBM latency exposed (ncu r02: 12 % of all warp samples on their first use).
+                // Each consumed slot is refilled with the chunk two ahead; chunks 2 and 3 free the slots for the next job.
+                const Job3 jn = prm.prog.job[j + 1 < kBwd3Jobs ? j + 1 : j];
+                const uint8_t* hrow_next = saved_row(gj, jn.slot, ((jn.flags & JB_HI_HALF) ? 128u : 0u) + cl);
                 if (j + 3 <= kBwd3Jobs) prefetch_seq(gj, j + 3);            // the job after next, into L2 (one line per thread)
                 unsigned long long tj0 = 0;
                 if (tracing) tj0 = clock64();
@@ -330,6 +338,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                     if (cc == 0 && (f & JB_WAIT_SF)) { mbar_wait(bar(kB3StageFree + 2 * team + (q >> 1)), ph_sf); ph_sf ^= 1; }
                     const H32 hp = hh[cc & 1];
                     if (cc < 2) hh[cc & 1] = ldg_nc_32B(hrow + pair_off(cc + 2, swz));       // refill with chunk cc + 2
+                    else if (j + 1 < kBwd3Jobs) hh[cc & 1] = ldg_nc_32B(hrow_next + pair_off(cc - 2, swz));      // next job's chunk cc - 2
                     chunk16(dpk, hp.a, hp.b, relu, write, row_addr, swz, cc, s1, s2);
                 }
                 if (write || hi) publish((hi ? kB3ActHi : kB3ActLo) + team);

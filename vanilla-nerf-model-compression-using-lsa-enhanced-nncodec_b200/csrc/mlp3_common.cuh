@@ -11,8 +11,10 @@ namespace nerfq {
 // warps 0, 2: weight loaders (warp 0 owns TMEM)   warps 1, 3: MMA issuers of half A and half B
 // warps 4..19: epilogue; a warp may only touch TMEM lanes 32*(warp % 4).., so warp w owns lane quarter q = w & 3 and
 // point quarter pq = (w - 4) >> 2.
-// Registers: 20 warps are launched with 96 registers each; the control warp group then releases registers
-// (setmaxnreg.dec) and the four epilogue warp groups claim them (setmaxnreg.inc) -- see kRegsCtrl3 / kRegsEpi3.
+// Registers: 20 warps are launched with 96 registers each (640 x 96 = 61440: the CTA's pool); the control warp group then
+// releases registers (setmaxnreg.dec) and the four epilogue warp groups claim them (setmaxnreg.inc).  The exchange happens
+// inside the CTA's launch allocation, so 4*32*ctrl + 16*32*epi <= 61440: with 64 for the control warps 104 is the most an
+// epilogue thread can get (112 was tried: the allocation never succeeds and the kernel hangs at start-up).
 constexpr int kCtrlWarps3 = 4;
 #define NERFQ_REGS_CTRL3 "64"
 #define NERFQ_REGS_EPI3 "104"
@@ -98,7 +100,7 @@ __device__ __forceinline__ void loader3(uint32_t sbase, const uint8_t* img, int 
         for (int c = 0; c < n_chunks; ++c, ++seq, src += kChunk3Bytes) {
             if ((int)(seq % kLoaders3) != which) continue;
             const uint32_t slot = seq & (kSlots3 - 1), par = (seq >> 2) & 1;
-            mbar_wait(bar(kB3WEmpty) + 8 * slot, par ^ 1);
+            mbar_wait_relaxed(bar(kB3WEmpty) + 8 * slot, par ^ 1);
             if (elect_one()) {
                 mbar_arrive_expect_tx(bar(kB3WFull) + 8 * slot, kChunk3Bytes);
                 bulk_g2s(sbase + kS3Ring + slot * kChunk3Bytes, src, kChunk3Bytes, bar(kB3WFull) + 8 * slot);
@@ -336,6 +338,30 @@ __device__ __forceinline__ float column_reduce16_3(float (&p)[16], int lane) {
     }
     const bool hi = lane & 2;
     const float r = (hi ? q2[1] : q2[0]) + __shfl_xor_sync(0xffffffffu, hi ? q2[0] : q2[1], 2);
+    return r + __shfl_xor_sync(0xffffffffu, r, 1);
+}
+
+// The same for 16 per-lane INTEGER columns (fixed-point terms: integer addition is associative, so the result does not depend
+// on the butterfly's order): 15 shuffles instead of 16 warp-wide REDUX, which issue at a fraction of the shuffle rate.
+__device__ __forceinline__ int column_reduce16_i3(int (&p)[16], int lane) {
+    int q8[8], q4[4], q2[2];
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q8[i] = (hi ? p[i + 8] : p[i]) + __shfl_xor_sync(0xffffffffu, hi ? p[i] : p[i + 8], 16);
+    }
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q4[i] = (hi ? q8[i + 4] : q8[i]) + __shfl_xor_sync(0xffffffffu, hi ? q8[i] : q8[i + 4], 8);
+    }
+    {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) q2[i] = (hi ? q4[i + 2] : q4[i]) + __shfl_xor_sync(0xffffffffu, hi ? q4[i] : q4[i + 2], 4);
+    }
+    const bool hi = lane & 2;
+    const int r = (hi ? q2[1] : q2[0]) + __shfl_xor_sync(0xffffffffu, hi ? q2[0] : q2[1], 2);
     return r + __shfl_xor_sync(0xffffffffu, r, 1);
 }
 

@@ -27,6 +27,8 @@
 // profiles/r01_umma_rate2_bulk_store_vs_mma.log.)
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "mlp3_common.cuh"
 
 namespace nerfq {
@@ -48,7 +50,10 @@ struct Fwd3Params {
 };
 
 constexpr float kAlphaFix = 262144.0f;       // 2^18: fixed-point unit of the alpha-head sum (int32: +-8192 logit units)
-constexpr int kSaveInJob = 2;      // chunks (of 4) whose saved activations are stored from registers inside the job; measured 1: 1.04, 2: 0.97, 3: 0.99, 4: 1.04 ms
+#ifndef NERFQ_SAVE_IN_JOB
+#define NERFQ_SAVE_IN_JOB 2
+#endif
+constexpr int kSaveInJob = NERFQ_SAVE_IN_JOB;      // chunks (of 4) whose saved activations are stored from registers inside the job; measured 1: 1.04, 2: 0.97, 3: 0.99, 4: 1.04 ms
 
 template <bool kSave, bool kTrace>
 __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid_constant__ Fwd3Params prm) {
@@ -68,12 +73,17 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
     const int first = blockIdx.x, stride = gridDim.x;
     const int n_iters = first < prm.n_groups ? (prm.n_groups - first + stride - 1) / stride : 0;
 
-    if (warp == 0 || warp == 2) {
-        loader3(sbase, prm.packed + kOffFwd3Image, kFwd3Chunks, n_iters, warp >> 1);
-    } else if (warp == 1 || warp == 3) {
-        if (n_iters > 0) issuer3<true, kTrace>(sbase, tmem_base, n_iters, (uint32_t)(warp >> 1), prm.dbg);
-    } else if (warp >= kCtrlWarps3) {
+    if (warp < kCtrlWarps3) {
+        // the control warp group hands registers to the four epilogue warp groups (64 / 112 per thread)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " NERFQ_REGS_CTRL3 ";");
+        if (warp == 0 || warp == 2) {
+            loader3(sbase, prm.packed + kOffFwd3Image, kFwd3Chunks, n_iters, warp >> 1);
+        } else {
+            if (n_iters > 0) issuer3<true, kTrace>(sbase, tmem_base, n_iters, (uint32_t)(warp >> 1), prm.dbg);
+        }
+    } else {
         // ================= epilogue warps =================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " NERFQ_REGS_EPI3 ";");
         const int e = warp - kCtrlWarps3;
         const int q = warp & 3, pq = e >> 2;
         const int team = e >> 3;                  // half-group A (points 0..127) or B (128..255): own accumulators and barriers
@@ -139,7 +149,12 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                 const Job3 jb = prm.prog.job[j];
                 const uint32_t f = jb.flags;
                 const uint32_t hi = (f & JB_HI_HALF) ? 1u : 0u;
-                const uint32_t ch = 128u * hi + 32u * q + lane;              // this thread's channel within the layer
+                // per-thread geometry re-derived from the thread index inside the loop (a volatile read the compiler cannot
+                // hoist): hoisted address parts were spilled, and a local-memory reload per job costs hundreds of cycles here
+                uint32_t tid_j;
+                asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_j));
+                const uint32_t q_j = (tid_j >> 5) & 3u, pq_j = ((tid_j >> 5) - (uint32_t)kCtrlWarps3) >> 2;
+                const uint32_t ch = 128u * hi + 32u * q_j + (tid_j & 31u);   // this thread's channel within the layer
                 const float2 c = c_next;
                 const float wa = wa_next;
                 unsigned long long t0 = 0;
@@ -183,16 +198,18 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                 }
 
                 if (f & JB_DIR_BEFORE) {        // gamma(x) is dead once L5 has been accumulated
-                    if (role == 0 && !ab_pe) write_dir_enc(enc, pt, vd);
+                    if (role == 0 && !ab_pe) write_dir_enc(enc, (int)((((tid_j >> 5) - (uint32_t)kCtrlWarps3) >> 1) * 32u + (tid_j & 31u)), vd);
                 }
                 // ---- 4 chunks of 16 points: TMEM -> y = acc*es + b -> (ReLU) -> fp16 -> operand tile ----
                 // The load of chunk i+1 is in flight while chunk i is converted and stored.
                 const bool relu = f & JB_RELU;
-                const uint32_t row_addr = opaque_u32(act + (ch >> 3) * kKGroup3 + pq * kNGroup3 + (ch & 7u) * 128u);
+                const uint32_t row_addr = act + (ch >> 3) * kKGroup3 + pq_j * kNGroup3 + (ch & 7u) * 128u;
                 const uint32_t swz = (ch & 7u) << 4;
                 uint8_t* save_ch = kSave ? save_g + (size_t)jb.slot * kSave3SlotBytes + save3_offset(0, ch) : nullptr;
                 uint32_t va[16], vb[16];
-                auto process = [&](const uint32_t (&v)[16], int cc) {
+                // (relu_c / alpha_c are compile-time tags: the job's kind is decided ONCE, before its four chunks, instead of by
+                // two branches inside every chunk -- ncu r02 had 15 % of the epilogue's stall samples in branch resolution)
+                auto process = [&](const uint32_t (&v)[16], int cc, auto relu_c, auto alpha_c) {
                     float y[16];
                     uint32_t pk[8];
 #pragma unroll
@@ -200,7 +217,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                     if (ab_math) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) pk[i] = v[2 * i] ^ v[2 * i + 1];
-                    } else if (relu) {
+                    } else if (decltype(relu_c)::value) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) pk[i] = cvt_pack_f16_relu(y[2 * i], y[2 * i + 1]);
                     } else {
@@ -224,53 +241,53 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                     }
                     // the same 16 values go to the saved-activation slot: the warp's 32 channels are adjacent, 1 KB per store
                     if (kSave && cc < kSaveInJob) st_global_v8(save_ch + save3_offset(pq * 4 + cc, 0), pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
-                    if ((f & JB_ALPHA) && !ab_alpha) {
+                    if (decltype(alpha_c)::value && !ab_alpha) {
                         // Alpha head over this warp's 32 channels (L7 is a ReLU layer: the head sees max(y, 0)), in fixed
                         // point: each term  max(y,0) * level * (delta*scale) of the sigma logit is rounded to 2^-18, the
-                        // warp sum is one REDUX per point, and the eight partial sums of a point (4 warps x 2 halves) meet
+                        // warp sum is an integer shuffle butterfly, and the eight partial sums of a point (4 warps x 2 halves) meet
                         // in native integer shared-memory atomics.  Integer addition is associative, so sigma -- and with it
                         // every pixel -- is bit-reproducible (a float butterfly + float atomics, a compare-and-swap loop
                         // on sm_100, cost the same and were not).  Range +-8192 logit units (kAlphaFix; two's-complement partial
                         // sums may wrap, only the total must fit), rounding error 1.8e-5 rms over the 256 terms.
-                        int sum[16];
+                        int term[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) sum[i] = __reduce_add_sync(0xffffffffu, __float2int_rn(fmaxf(y[i], 0.0f) * wa));
-                        // lane l (< 16) keeps the sum of point l: select tree on the lane bits
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) sum[i] = (lane & 8) ? sum[i + 8] : sum[i];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) sum[i] = (lane & 4) ? sum[i + 4] : sum[i];
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) sum[i] = (lane & 2) ? sum[i + 2] : sum[i];
-                        const int mine = (lane & 1) ? sum[1] : sum[0];
-                        if (lane < 16) red_shared_add_s32(out_sa + 4 * (pq * 64 + cc * 16 + lane), mine);
+                        for (int i = 0; i < 16; ++i) term[i] = __float2int_rn(fmaxf(y[i], 0.0f) * wa);
+                        // transpose-and-add butterfly over the warp's 32 channels: lanes 2l and 2l+1 end up with point l's sum
+                        const int mine = column_reduce16_i3(term, lane);
+                        if (!(lane & 1)) red_shared_add_s32(out_sa + 4 * (pq * 64 + cc * 16 + (lane >> 1)), mine);
                     }
                 };
-                if (ab_ld) {
+                // The load of chunk i+1 is in flight while chunk i is converted and stored.
+                auto run4 = [&](auto relu_c, auto alpha_c) {
+                    if (ab_ld) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) va[i] = vb[i] = (uint32_t)(i + j);
-                    process(va, 0);
-                    process(vb, 1);
-                    process(va, 2);
-                    process(vb, 3);
-                } else {
-                    tmem_ld16(ta, va);
-                    tmem_ld_wait();
-                    tmem_ld16(ta + 16, vb);
-                    process(va, 0);
-                    tmem_ld_wait();
-                    tmem_ld16(ta + 32, va);
-                    process(vb, 1);
-                    tmem_ld_wait();
-                    tmem_ld16(ta + 48, vb);
-                    process(va, 2);
-                    tmem_ld_wait();
-                    process(vb, 3);
-                }
+                        for (int i = 0; i < 16; ++i) va[i] = vb[i] = (uint32_t)(i + j);
+                        process(va, 0, relu_c, alpha_c);
+                        process(vb, 1, relu_c, alpha_c);
+                        process(va, 2, relu_c, alpha_c);
+                        process(vb, 3, relu_c, alpha_c);
+                    } else {
+                        tmem_ld16(ta, va);
+                        tmem_ld_wait();
+                        tmem_ld16(ta + 16, vb);
+                        process(va, 0, relu_c, alpha_c);
+                        tmem_ld_wait();
+                        tmem_ld16(ta + 32, va);
+                        process(vb, 1, relu_c, alpha_c);
+                        tmem_ld_wait();
+                        tmem_ld16(ta + 48, vb);
+                        process(va, 2, relu_c, alpha_c);
+                        tmem_ld_wait();
+                        process(vb, 3, relu_c, alpha_c);
+                    }
+                };
+                if (f & JB_ALPHA) run4(std::true_type{}, std::true_type{});            // L7 (ReLU) + alpha head
+                else if (relu) run4(std::true_type{}, std::false_type{});
+                else run4(std::false_type{}, std::false_type{});                       // feature layer: no activation
                 if (tracing) { const unsigned long long dt = clock64() - t0; t_math += dt; if (j == j_sel) t_sel_math += dt; }
                 if (f & JB_PE_AFTER) {          // the direction stage of this group has been accumulated
                     if (g + stride < prm.n_groups) {
-                        if (!ab_pe) write_pe_half(enc, pt, role, p);
+                        if (!ab_pe) write_pe_half(enc, (int)((((tid_j >> 5) - (uint32_t)kCtrlWarps3) >> 1) * 32u + (tid_j & 31u)), role, p);
 #pragma unroll
                         for (int k = 0; k < 3; ++k) vd[k] = vd_next[k];
                     }

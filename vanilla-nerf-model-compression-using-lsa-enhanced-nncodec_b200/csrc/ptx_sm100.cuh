@@ -40,13 +40,28 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait comes back every ~50 cycles while the phase is incomplete: ncu r02 counted 25 polls per accumulator wait and
+// 28 % of all issued instructions in the poll loops.  A suspend-time hint (NERFQ_MBAR_SUSPEND_NS > 0) was measured and does
+// not help: 1, 4 and 20 us all ran 1 % SLOWER than no hint (profiles/r02_ab_wait_hint.log), so the default is none; waits
+// that are not latency-critical back off with nanosleep instead (mbar_wait_relaxed).
+#ifndef NERFQ_MBAR_SUSPEND_NS
+#define NERFQ_MBAR_SUSPEND_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+#if NERFQ_MBAR_SUSPEND_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)NERFQ_MBAR_SUSPEND_NS) : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
     return ok != 0;
 }
 // non-blocking probe (try_wait may suspend the thread for a while when the phase is not complete yet)
@@ -68,10 +83,35 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
     __trap();
     __builtin_unreachable();
 }
+// NERFQ_MBAR_POLL_UNROLL probes per pass of the bookkeeping (spin counter, limit check): a probe comes back after ~50 cycles
+// whether or not the phase completed, so the loop's own instructions -- 7 per probe when not unrolled -- are what a waiting
+// warp feeds into the scheduler it shares with working warps.
+#ifndef NERFQ_MBAR_POLL_UNROLL
+#define NERFQ_MBAR_POLL_UNROLL 4
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
+    for (;;) {
+#pragma unroll
+        for (int i = 0; i < NERFQ_MBAR_POLL_UNROLL; ++i)
+            if (mbar_try_wait(bar, parity)) return;
+        if (++spins > (threadIdx.x < 128 ? NERFQ_MBAR_SPIN_LIMIT / (8 * NERFQ_MBAR_POLL_UNROLL) : NERFQ_MBAR_SPIN_LIMIT / NERFQ_MBAR_POLL_UNROLL))
+            mbar_timeout(bar, parity);   // control warps report first
+    }
+}
+
+// For waits with slack (the weight loaders: a freed ring slot is needed again three chunks later): sleep between polls
+// instead of re-issuing the probe at full rate, which takes issue slots from the epilogue warps on the same scheduler.
+#ifndef NERFQ_RELAXED_WAIT_NS
+#define NERFQ_RELAXED_WAIT_NS 128
+#endif
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (threadIdx.x < 128 ? NERFQ_MBAR_SPIN_LIMIT / 8 : NERFQ_MBAR_SPIN_LIMIT)) mbar_timeout(bar, parity);   // control warps report first
+#if NERFQ_RELAXED_WAIT_NS > 0
+        __nanosleep(NERFQ_RELAXED_WAIT_NS);
+#endif
+        if (++spins > NERFQ_MBAR_SPIN_LIMIT / 8) mbar_timeout(bar, parity);
     }
 }
 
