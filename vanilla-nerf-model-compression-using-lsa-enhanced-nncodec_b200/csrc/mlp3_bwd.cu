@@ -79,12 +79,13 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
     const int first = blockIdx.x, stride = gridDim.x;
     const int n_iters = first < prm.n_groups ? (prm.n_groups - first + stride - 1) / stride : 0;
 
-    if (warp < kCtrlWarps3) {
+    if (warp >= kCtrlWarp0 && warp < kCtrlWarp0 + kCtrlWarps3) {
+        const int cw = warp - kCtrlWarp0;
         asm volatile("setmaxnreg.dec.sync.aligned.u32 " NERFQ_REGS_CTRL3 ";");
-        if (warp == 0 || warp == 2) {
-            loader3(sbase, prm.packed + kOffBwd3Image, kBwd3Chunks, n_iters, warp >> 1);
+        if (cw == 0 || cw == 2) {
+            loader3(sbase, prm.packed + kOffBwd3Image, kBwd3Chunks, n_iters, cw >> 1);
         } else {
-            if (n_iters > 0) issuer3<false, kTrace>(sbase, tmem_base, n_iters, (uint32_t)(warp >> 1), prm.dbg);
+            if (n_iters > 0) issuer3<false, kTrace>(sbase, tmem_base, n_iters, (uint32_t)(cw >> 1), prm.dbg);
         }
     } else {
         // ================= epilogue warps =================
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
         // the role dispatch above uses the shuffled (uniform-register) warp index; the per-thread geometry below is derived
         // from threadIdx so that the compiler rematerialises it from the special register rather than spilling it
         const int tw = (int)(threadIdx.x >> 5);
-        const int e = tw - kCtrlWarps3;
+        const int e = tw - kEpiWarp0;
         // All 16 warps work on one job at a time (a job is latency- not issue-bound, so halving the points per warp
         // halves its duration; two 8-warp teams running both jobs of a step concurrently measured slower).  A warp owns
         // lane quarter q and point quarter pq (64 points = 4 chunks of 16) of both accumulators.

@@ -73,18 +73,19 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
     const int first = blockIdx.x, stride = gridDim.x;
     const int n_iters = first < prm.n_groups ? (prm.n_groups - first + stride - 1) / stride : 0;
 
-    if (warp < kCtrlWarps3) {
+    if (warp >= kCtrlWarp0 && warp < kCtrlWarp0 + kCtrlWarps3) {
+        const int cw = warp - kCtrlWarp0;
         // the control warp group hands registers to the four epilogue warp groups (64 / 112 per thread)
         asm volatile("setmaxnreg.dec.sync.aligned.u32 " NERFQ_REGS_CTRL3 ";");
-        if (warp == 0 || warp == 2) {
-            loader3(sbase, prm.packed + kOffFwd3Image, kFwd3Chunks, n_iters, warp >> 1);
+        if (cw == 0 || cw == 2) {
+            loader3(sbase, prm.packed + kOffFwd3Image, kFwd3Chunks, n_iters, cw >> 1);
         } else {
-            if (n_iters > 0) issuer3<true, kTrace>(sbase, tmem_base, n_iters, (uint32_t)(warp >> 1), prm.dbg);
+            if (n_iters > 0) issuer3<true, kTrace>(sbase, tmem_base, n_iters, (uint32_t)(cw >> 1), prm.dbg);
         }
     } else {
         // ================= epilogue warps =================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 " NERFQ_REGS_EPI3 ";");
-        const int e = warp - kCtrlWarps3;
+        const int e = warp - kEpiWarp0;
         const int q = warp & 3, pq = e >> 2;
         const int team = e >> 3;                  // half-group A (points 0..127) or B (128..255): own accumulators and barriers
         const uint32_t tmem_lane = tmem_base + (uint32_t(q * 32) << 16) + team * 256 + (pq & 1) * 64;
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                 // hoist): hoisted address parts were spilled, and a local-memory reload per job costs hundreds of cycles here
                 uint32_t tid_j;
                 asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_j));
-                const uint32_t q_j = (tid_j >> 5) & 3u, pq_j = ((tid_j >> 5) - (uint32_t)kCtrlWarps3) >> 2;
+                const uint32_t q_j = (tid_j >> 5) & 3u, pq_j = ((tid_j >> 5) - (uint32_t)kEpiWarp0) >> 2;
                 const uint32_t ch = 128u * hi + 32u * q_j + (tid_j & 31u);   // this thread's channel within the layer
                 const float2 c = c_next;
                 const float wa = wa_next;
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                 }
 
                 if (f & JB_DIR_BEFORE) {        // gamma(x) is dead once L5 has been accumulated
-                    if (role == 0 && !ab_pe) write_dir_enc(enc, (int)((((tid_j >> 5) - (uint32_t)kCtrlWarps3) >> 1) * 32u + (tid_j & 31u)), vd);
+                    if (role == 0 && !ab_pe) write_dir_enc(enc, (int)((((tid_j >> 5) - (uint32_t)kEpiWarp0) >> 1) * 32u + (tid_j & 31u)), vd);
                 }
                 // ---- 4 chunks of 16 points: TMEM -> y = acc*es + b -> (ReLU) -> fp16 -> operand tile ----
                 // The load of chunk i+1 is in flight while chunk i is converted and stored.
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                 if (tracing) { const unsigned long long dt = clock64() - t0; t_math += dt; if (j == j_sel) t_sel_math += dt; }
                 if (f & JB_PE_AFTER) {          // the direction stage of this group has been accumulated
                     if (g + stride < prm.n_groups) {
-                        if (!ab_pe) write_pe_half(enc, (int)((((tid_j >> 5) - (uint32_t)kCtrlWarps3) >> 1) * 32u + (tid_j & 31u)), role, p);
+                        if (!ab_pe) write_pe_half(enc, (int)((((tid_j >> 5) - (uint32_t)kEpiWarp0) >> 1) * 32u + (tid_j & 31u)), role, p);
 #pragma unroll
                         for (int k = 0; k < 3; ++k) vd[k] = vd_next[k];
                     }

@@ -83,11 +83,12 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
     __trap();
     __builtin_unreachable();
 }
-// NERFQ_MBAR_POLL_UNROLL probes per pass of the bookkeeping (spin counter, limit check): a probe comes back after ~50 cycles
-// whether or not the phase completed, so the loop's own instructions -- 7 per probe when not unrolled -- are what a waiting
-// warp feeds into the scheduler it shares with working warps.
+// NERFQ_MBAR_POLL_UNROLL probes per pass of the bookkeeping (spin counter, limit check).  A probe comes back after ~50 cycles
+// whether or not the phase completed, so the loop's own 7 instructions per probe are what a waiting warp feeds into the
+// scheduler it shares with working warps -- yet 4 probes per pass measured 7 % SLOWER on the forward kernel than 1
+// (0.746 vs 0.694 ms, profiles/r02_ab_poll_and_save_split.log), so the loop stays rolled.
 #ifndef NERFQ_MBAR_POLL_UNROLL
-#define NERFQ_MBAR_POLL_UNROLL 4
+#define NERFQ_MBAR_POLL_UNROLL 1
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
@@ -96,7 +97,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         for (int i = 0; i < NERFQ_MBAR_POLL_UNROLL; ++i)
             if (mbar_try_wait(bar, parity)) return;
         if (++spins > (threadIdx.x < 128 ? NERFQ_MBAR_SPIN_LIMIT / (8 * NERFQ_MBAR_POLL_UNROLL) : NERFQ_MBAR_SPIN_LIMIT / NERFQ_MBAR_POLL_UNROLL))
-            mbar_timeout(bar, parity);   // control warps report first
+            mbar_timeout(bar, parity);   // (the thread-dependent limit also keeps ptxas from restructuring the wait loops: with a constant limit the issuer code spilled)
     }
 }
 
