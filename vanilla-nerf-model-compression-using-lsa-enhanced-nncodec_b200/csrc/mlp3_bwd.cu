@@ -41,7 +41,10 @@ constexpr uint32_t kS3BwdGa = kS3BwdPg + 4096;          // float ga[256]: alpha-
 constexpr uint32_t kS3BwdMax = kS3BwdGa + 1024;         // per half (16 bytes each): uint gmax[2], float rinv, int group
 static_assert(kS3BwdMax + 32 <= kS3Misc, "backward scratch must fit the encoding-tile region");
 
-// one 128-byte line into L2
+#ifndef NERFQ_BWD_PREFETCH
+#define NERFQ_BWD_PREFETCH 1
+#endif
+// the 64 bytes (L2 fill granularity) around p into L2
 __device__ __forceinline__ void prefetch_l2_line(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p) : "memory");
 }
@@ -160,8 +163,13 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
         // (mlp3_layout.h, Prog3Bwd::slice_off) is 16 pieces of 4 KB (128 channels x 32 B), one per point chunk, 8 KB
         // apart: 512 lines, one per thread.
         const uint32_t pf_thread = (uint32_t)e * 8192u + (uint32_t)lane * 128u;
+        // (one request per 128-byte line.  The L2 fills 64 bytes per miss, so this covers half of every slice -- ncu r02 counted
+        // exactly 50 % of the demand loads' sectors as L2 misses -- but requesting both halves, NERFQ_BWD_PREFETCH = 2, measured
+        // 5 % SLOWER (0.953 vs 0.906 ms) and no prefetch at all 1 % slower: profiles/r02_ab_prefetch_and_saver_waits.log)
         auto prefetch_seq = [&](int g, int v) {      // v: index into [views, job 0 .. 17]
-            prefetch_l2_line(prm.save + (size_t)g * kSave3GroupBytes + (pf_thread + prm.prog.slice_off[v]));
+            const uint8_t* line = prm.save + (size_t)g * kSave3GroupBytes + (pf_thread + prm.prog.slice_off[v]);
+            if (NERFQ_BWD_PREFETCH >= 1) prefetch_l2_line(line);
+            if (NERFQ_BWD_PREFETCH >= 2) prefetch_l2_line(line + 64);
         };
         float2 c_next = make_float2(1.f, 0.f);
         if (n_iters > 0) {
