@@ -1,6 +1,6 @@
 """Multi-GPU plumbing (one process per GPU, torch.distributed over NCCL): rays are independent units, so
 test-view rendering shards the pixel range with no data-path collective, and data-parallel LSA tuning needs
-one all-reduce of the scale gradients per network and step (2 x 19.5 KB of 64-bit fixed-point sums).  The reference itself is single-GPU
+one all-reduce of the scale gradients per step (39 KB of 64-bit fixed-point sums, both networks).  The reference itself is single-GPU
 (README.md:76); SURVEY section 8(e) defines this sharding."""
 from typing import Optional, Tuple
 

@@ -143,13 +143,12 @@ def _forward_pipeline(cfg: _Cfg, sc0, sc1, save: bool):
 
 
 class _DPState:
-    """Per-device scratch of the data-parallel backward: the two networks' fixed-point gradient buffers (kept zeroed by
-    nerfq_mlp_backward_finalize) and the side stream the fine network's all-reduce runs on."""
+    """Per-device scratch of the data-parallel backward: the two networks' fixed-point gradient buffers, contiguous so
+    that one all-reduce covers both (kept zeroed by nerfq_mlp_backward_finalize)."""
     _by_device = {}
 
     def __init__(self, dev):
         self.fix = torch.zeros((2, ops.grad_fix_elems()), dtype=torch.int64, device=dev)
-        self.side = torch.cuda.Stream(device=dev)
 
     @classmethod
     def get(cls, dev):
@@ -167,8 +166,8 @@ def _backward_pipeline(cfg: _Cfg, st: dict, d_rgb1, d_rgb0, g_out: Optional[torc
 
     Data parallel (DATA_PARALLEL['enabled'], one process per GPU): every rank's kernels leave s*ds as 64-bit FIXED-POINT
     sums; those are all-reduced as integers (NCCL int64 sum, 19.5 KB per network) before the conversion to float, so the
-    result does not depend on how the batch is split over ranks.  The fine network's all-reduce runs on a side stream under
-    the coarse network's backward kernels; only the coarse network's is exposed."""
+    result does not depend on how the batch is split over ranks.  Both networks' buffers go through one all-reduce after the
+    last backward kernel."""
     mc = TUNING["max_ctas"]
     rays = cfg.rays
     dev = rays.device
@@ -190,24 +189,17 @@ def _backward_pipeline(cfg: _Cfg, st: dict, d_rgb1, d_rgb0, g_out: Optional[torc
     import torch.distributed as dist
     group = DATA_PARALLEL.get("group")
     dps = _DPState.get(dev)
-    main = torch.cuda.current_stream(dev)
-    pending = []                                  # slots whose all-reduce is in flight on the side stream
-    for i, (pn, raw, z, save, noise, d_rgb, slot) in enumerate(passes):
+    slots = []
+    for pn, raw, z, save, noise, d_rgb, slot in passes:
         d_raw = ops.composite_bwd(raw, z, rays, cfg.white, d_rgb.contiguous(), noise)
         ops.mlp_backward_partial(pn, d_raw, raw, save, dps.fix[slot], max_ctas=mc)
-        last = i + 1 == len(passes)
-        shared = not last and passes[i + 1][6] == slot          # the next pass accumulates into the same buffer
-        if shared:
-            continue
-        if last:
-            dist.all_reduce(dps.fix[slot], op=dist.ReduceOp.SUM, group=group)
-        else:
-            dps.side.wait_stream(main)
-            with torch.cuda.stream(dps.side):
-                dist.all_reduce(dps.fix[slot], op=dist.ReduceOp.SUM, group=group)
-            pending.append(slot)
-    if pending:
-        main.wait_stream(dps.side)
+        if slot not in slots:
+            slots.append(slot)
+    # ONE all-reduce for both networks (39 KB of int64).  Overlapping the fine network's all-reduce with the coarse
+    # network's backward on a side stream was tried in round 2 and bought nothing: the persistent backward kernel holds
+    # every SM, so NCCL's kernel only got an SM when that kernel ended, and the two all-reduces ran back to back at the
+    # tail anyway (0.082 ms exposed at N = 8, 2 x 0.030 ms alone).
+    dist.all_reduce(dps.fix if len(slots) == 2 else dps.fix[slots[0]], op=dist.ReduceOp.SUM, group=group)
     done = set()
     for pn, _, _, _, _, _, slot in passes:
         if slot not in done:
