@@ -373,8 +373,19 @@ __device__ __forceinline__ void red_shared_add_f32(uint32_t addr, float v) {
 // 32-byte global store (one full sector; a warp of consecutive addresses writes eight full lines)
 __device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1,
                                              uint32_t b2, uint32_t b3) {
+#ifndef NERFQ_SAVE_ST_POLICY
+#define NERFQ_SAVE_ST_POLICY 0
+#endif
+#if NERFQ_SAVE_ST_POLICY == 0
     asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3) : "memory");
+#elif NERFQ_SAVE_ST_POLICY == 1
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3) : "memory");
+#else
+    asm volatile("st.global.L1::no_allocate.L2::evict_last.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3) : "memory");
+#endif
 }
 // {lo, hi} -> packed fp16 pair, round to nearest, saturating at +-65504 instead of producing inf (one F2FP either way);
 // the relu form clamps negative inputs to +0 in the same instruction
