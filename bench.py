@@ -40,7 +40,7 @@ METRIC = "rays/sec render_rays (64+128 samples/ray); LSA steps/sec"
 WORKLOAD = ("cfg2: LSA fine-tuning step at qp=-20 (quantise -> LSA-scaled dequant -> render 4096 rays/GPU, 64+128 samples -> "
             "backward into LSA scales -> Adam), random-init vanilla NeRF, synthetic rays")
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 4096 rays x 192 samples (profiles/)
-NCU_DRAM_BYTES = {"mlp_bwd_fine": 3917792000 + 13829888, "mlp_fwd_fine": 4663552 + 3803394000}      # profiles/r01_ncu_mlp_kernels_summary.txt
+NCU_DRAM_BYTES = {"mlp_bwd_fine": 3869400000 + 3700000, "mlp_fwd_fine": 4700000 + 3780200000}      # profiles/r02_ncu_mlp_kernels_summary.txt
 
 
 def synth_batch(n, seed, device="cpu"):
@@ -361,12 +361,15 @@ def run_cuda(args):
             dom = max(("mlp_fwd_fine", "mlp_bwd_fine"), key=lambda k: rows[k]["ms"])
             # the kernels are timed alone (10 back-to-back launches), so the denominator is the BURST bf16 figure;
             # `traffic` = dram__bytes_read+write of one launch of this kernel from the committed ncu --set full capture
-            # (profiles/r01_ncu_mlp_kernels_summary.txt), not a live measurement
+            # (profiles/r02_ncu_mlp_kernels_summary.txt), not a live measurement.  The two LSA kernels are co-limited: they also
+            # move ~3.8 GB per launch, so the same launch is reported against the HBM roofline (`hbm_*`).
             line["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": rows[dom]["tflops"], "peak": pk["tensor_burst"], "unit": "TFLOP/s",
                                 "frac": rows[dom]["tflops"] / pk["tensor_burst"], "traffic": NCU_DRAM_BYTES.get(dom),
                                 "peak_source": pk["source"] + " (burst bf16: kernel timed alone)",
                                 "frac_of_sustained": rows[dom]["tflops"] / pk["tensor"],
                                 "algorithmic_flop_per_launch": kern[dom][1],
+                                "hbm_achieved_gbs": NCU_DRAM_BYTES[dom] / (rows[dom]["ms"] * 1e-3) / 1e9, "hbm_peak_gbs": pk["hbm"],
+                                "hbm_frac": NCU_DRAM_BYTES[dom] / (rows[dom]["ms"] * 1e-3) / 1e9 / pk["hbm"],
                                 "share_of_step": rows[dom]["ms"] / ms_norequant, "mlp_kernels_share_of_step": step_kernel_ms / ms_norequant}
             line["kernels"] = rows
             # CPU baseline: the oracle port on this box's host cores, bounded sample

@@ -81,7 +81,7 @@ def test_sample_pdf_golden(dev):
     close(ops.sample_pdf(bins, wts, 128, torch.from_numpy(g["pdf_u"]).to(dev)), g["pdf_rnd"], 2e-5)
 
 
-@pytest.mark.parametrize("S,Ni", [(64, 128), (64, 64), (17, 5), (128, 128)])
+@pytest.mark.parametrize("S,Ni", [(64, 128), (64, 64), (17, 5), (128, 128), (24, 40), (30, 33), (64, 100)])      # 1, 2, 4, 8 values per lane in the register sort; sizes that are not multiples of 4
 def test_sample_fine_oracle(dev, S, Ni):
     ops = _ops()
     from oracle import render_oracle as ro

@@ -306,8 +306,8 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 if (j + 3 <= kBwd3Jobs) prefetch_seq(gj, j + 3);            // the job after next, into L2 (one line per thread)
                 unsigned long long tj0 = 0;
                 if (tracing) tj0 = clock64();
-                if (hi) { mbar_wait(bar(kB3AccReady + 2 * team + 1), ph_acc1); ph_acc1 ^= 1; }
-                else { mbar_wait(bar(kB3AccReady + 2 * team), ph_acc0); ph_acc0 ^= 1; }
+                if (hi) { mbar_wait_acc(bar(kB3AccReady + 2 * team + 1), ph_acc1); ph_acc1 ^= 1; }
+                else { mbar_wait_acc(bar(kB3AccReady + 2 * team), ph_acc0); ph_acc0 ^= 1; }
                 tc_fence_after_sync();
                 if (tracing) { const unsigned long long t = clock64(); t_acc += t - tj0; tj0 = t; }
                 c_next = __ldg(&g_sb[prm.prog.job[j + 1 < kBwd3Jobs ? j + 1 : 0].ch + cl]);        // in flight during this job

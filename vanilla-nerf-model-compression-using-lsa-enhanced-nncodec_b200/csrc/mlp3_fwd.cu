@@ -160,8 +160,8 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                 const float wa = wa_next;
                 unsigned long long t0 = 0;
                 if (tracing) t0 = clock64();
-                if (f & JB_ACC_HI) { mbar_wait(bar(kB3AccReady + 2 * team + 1), ph_acc1); ph_acc1 ^= 1; }
-                else { mbar_wait(bar(kB3AccReady + 2 * team), ph_acc0); ph_acc0 ^= 1; }
+                if (f & JB_ACC_HI) { mbar_wait_acc(bar(kB3AccReady + 2 * team + 1), ph_acc1); ph_acc1 ^= 1; }
+                else { mbar_wait_acc(bar(kB3AccReady + 2 * team), ph_acc0); ph_acc0 ^= 1; }
                 tc_fence_after_sync();
                 if (tracing) { const unsigned long long t1 = clock64(); t_acc += t1 - t0; t0 = t1; }
                 const uint32_t ta = tmem_lane + ((f & JB_ACC_HI) ? 128u : 0u);

@@ -116,6 +116,23 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
     }
 }
 
+// The epilogue warps' wait for an accumulator: latency-critical (the job starts when it returns), but 16 warps polling
+// at full rate are a quarter of all issued instructions.  NERFQ_ACC_WAIT_NS > 0 sleeps that long between probes.
+#ifndef NERFQ_ACC_WAIT_NS
+#define NERFQ_ACC_WAIT_NS 0
+#endif
+__device__ __forceinline__ void mbar_wait_acc(uint32_t bar, uint32_t parity) {
+#if NERFQ_ACC_WAIT_NS > 0
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(NERFQ_ACC_WAIT_NS);
+        if (++spins > NERFQ_MBAR_SPIN_LIMIT) mbar_timeout(bar, parity);
+    }
+#else
+    mbar_wait(bar, parity);
+#endif
+}
+
 // One lane of a converged warp (the compiler keeps warp-uniform operands of the elected code in uniform registers).
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;

@@ -9,6 +9,8 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace nerfq {
 
 constexpr int kWarpsPerBlock = 8;
@@ -88,19 +90,24 @@ __global__ void coarse_depths_kernel(const float* __restrict__ rays, const float
 // ---------------------------------------------------------------------------------------------
 // compositing
 // ---------------------------------------------------------------------------------------------
+// PER = samples per lane, a compile-time constant (ceil(S / 32): 2 for the coarse pass, 6 for the fine one): with a
+// run-time bound every loop below ran all 8 slots -- 4x the work at S = 64 -- and kept 8 slots of every array live
+// (round 2: composite_fwd at 32768 rays 32.8 -> see profiles/r02_ncu_ray_kernels_summary.txt).
+template <int PER>
 struct RaySeg {
-    float alpha[kMaxPerLane], dist[kMaxPerLane], sig[kMaxPerLane], zz[kMaxPerLane];
-    float c[kMaxPerLane][3];
+    float alpha[PER], dist[PER], sig[PER], zz[PER];
+    float c[PER][3];
 };
 
 // Loads this lane's contiguous segment [lane*per, lane*per+per) of one ray and evaluates alpha / colour.
-__device__ __forceinline__ void load_segment(RaySeg& s, const float* __restrict__ raw, const float* __restrict__ z,
-                                             const float* __restrict__ noise, float dnorm, int S, int per, int lane) {
-    const int i0 = lane * per;
+template <int PER>
+__device__ __forceinline__ void load_segment(RaySeg<PER>& s, const float* __restrict__ raw, const float* __restrict__ z,
+                                             const float* __restrict__ noise, float dnorm, int S, int lane) {
+    const int i0 = lane * PER;
 #pragma unroll
-    for (int k = 0; k < kMaxPerLane; ++k) {
+    for (int k = 0; k < PER; ++k) {
         const int i = i0 + k;
-        if (k < per && i < S) {
+        if (i < S) {
             const float4 r = *reinterpret_cast<const float4*>(raw + 4 * i);
             const float zi = z[i];
             const float gap = (i + 1 < S) ? __fsub_rn(z[i + 1], zi) : 1e10f;
@@ -121,6 +128,7 @@ __device__ __forceinline__ void load_segment(RaySeg& s, const float* __restrict_
     }
 }
 
+template <int PER>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock) composite_fwd_kernel(
     const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays, const float* __restrict__ noise,
     int white_bkgd, long long n_rays, int S, float* __restrict__ rgb, float* __restrict__ disp, float* __restrict__ acc,
@@ -128,21 +136,20 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) composite_fwd_kernel(
     const int lane = threadIdx.x & 31;
     const long long ray = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (ray >= n_rays) return;
-    const int per = (S + 31) / 32;
+    constexpr int per = PER;
     const float* r = rays + ray * 11;
     const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(r[3], r[3]), __fmul_rn(r[4], r[4])), __fmul_rn(r[5], r[5])));
-    RaySeg s;
-    load_segment(s, raw + ray * S * 4, z + ray * S, noise ? noise + ray * S : nullptr, dnorm, S, per, lane);
+    RaySeg<PER> s;
+    load_segment<PER>(s, raw + ray * S * 4, z + ray * S, noise ? noise + ray * S : nullptr, dnorm, S, lane);
     float prod = 1.0f;
 #pragma unroll
-    for (int k = 0; k < kMaxPerLane; ++k)
-        if (k < per) prod *= __fadd_rn(__fsub_rn(1.0f, s.alpha[k]), 1e-10f);
+    for (int k = 0; k < PER; ++k) prod *= __fadd_rn(__fsub_rn(1.0f, s.alpha[k]), 1e-10f);
     float T = warp_excl_prod(prod, lane);
     float a_rgb[3] = {0.f, 0.f, 0.f}, a_depth = 0.f, a_acc = 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxPerLane; ++k) {
+    for (int k = 0; k < PER; ++k) {
         const int i = lane * per + k;
-        if (k < per && i < S) {
+        if (i < S) {
             const float w = __fmul_rn(s.alpha[k], T);
             T *= __fadd_rn(__fsub_rn(1.0f, s.alpha[k]), 1e-10f);
             if (weights) weights[ray * S + i] = w;
@@ -170,41 +177,39 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) composite_fwd_kernel(
 }
 
 // d_raw from d_rgb (the only output the LSA objective uses, run_nerf.py:741-751).
+template <int PER>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock) composite_bwd_kernel(
     const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays, const float* __restrict__ noise,
     int white_bkgd, const float* __restrict__ d_rgb, long long n_rays, int S, float* __restrict__ d_raw) {
     const int lane = threadIdx.x & 31;
     const long long ray = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (ray >= n_rays) return;
-    const int per = (S + 31) / 32;
+    constexpr int per = PER;
     const float* r = rays + ray * 11;
     const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(r[3], r[3]), __fmul_rn(r[4], r[4])), __fmul_rn(r[5], r[5])));
-    RaySeg s;
-    load_segment(s, raw + ray * S * 4, z + ray * S, noise ? noise + ray * S : nullptr, dnorm, S, per, lane);
+    RaySeg<PER> s;
+    load_segment<PER>(s, raw + ray * S * 4, z + ray * S, noise ? noise + ray * S : nullptr, dnorm, S, lane);
     const float g0 = d_rgb[ray * 3 + 0], g1 = d_rgb[ray * 3 + 1], g2 = d_rgb[ray * 3 + 2];
     const float gbg = white_bkgd ? (g0 + g1 + g2) : 0.0f;
     float prod = 1.0f;
 #pragma unroll
-    for (int k = 0; k < kMaxPerLane; ++k)
-        if (k < per) prod *= __fadd_rn(__fsub_rn(1.0f, s.alpha[k]), 1e-10f);
+    for (int k = 0; k < PER; ++k) prod *= __fadd_rn(__fsub_rn(1.0f, s.alpha[k]), 1e-10f);
     float T = warp_excl_prod(prod, lane);
-    float Tk[kMaxPerLane], wk[kMaxPerLane], dwk[kMaxPerLane];
+    float Tk[PER], wk[PER], dwk[PER];
     float seg = 0.0f;
 #pragma unroll
-    for (int k = 0; k < kMaxPerLane; ++k) {
+    for (int k = 0; k < PER; ++k) {
         Tk[k] = T;
         wk[k] = s.alpha[k] * T;
         dwk[k] = g0 * s.c[k][0] + g1 * s.c[k][1] + g2 * s.c[k][2] - gbg;     // dL/dw_i
-        if (k < per) {
-            T *= __fadd_rn(__fsub_rn(1.0f, s.alpha[k]), 1e-10f);
-            seg += dwk[k] * wk[k];
-        }
+        T *= __fadd_rn(__fsub_rn(1.0f, s.alpha[k]), 1e-10f);
+        seg += dwk[k] * wk[k];
     }
     float suffix = warp_excl_suffix_sum(seg, lane);      // sum over later lanes of dw*w
 #pragma unroll
-    for (int k = kMaxPerLane - 1; k >= 0; --k) {
+    for (int k = PER - 1; k >= 0; --k) {
         const int i = lane * per + k;
-        if (k < per && i < S) {
+        if (i < S) {
             const float a = __fadd_rn(__fsub_rn(1.0f, s.alpha[k]), 1e-10f);
             const float dalpha = dwk[k] * Tk[k] - suffix / a;
             const float dsig = (s.sig[k] > 0.0f) ? dalpha * s.dist[k] * (1.0f - s.alpha[k]) : 0.0f;
@@ -262,7 +267,9 @@ __device__ __forceinline__ void warp_bitonic_sort(float (&v)[PER], int lane) {
 // importance sampling + merge
 // ---------------------------------------------------------------------------------------------
 // One warp per ray.  Shared memory per warp: cdf[S-1], bins[S-1], sort buffer[P] with P = pow2 >= S+Ni.
-template <int PER>
+// PER: values per lane in the final sort (32 * PER >= S + Ni); WMAX: power-of-two bound on the interior weights per lane
+// ((S - 2 + 31) / 32 <= WMAX): the pdf / cdf loops run WMAX slots instead of 8.
+template <int PER, int WMAX>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_fine_kernel(
     const float* __restrict__ z_coarse, const float* __restrict__ bins_in, const float* __restrict__ weights,
     const float* __restrict__ u_in, long long n_rays, int S, int Ni, int P, float* __restrict__ z_out, float* __restrict__ z_std,
@@ -280,10 +287,10 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_fine_kernel(
     // pdf over the S-2 interior weights, cdf = [0, cumsum]
     const int nw = S - 2;
     const int per = (nw + 31) / 32;
-    float loc[kMaxPerLane];
+    float loc[WMAX];
     float lsum = 0.0f;
 #pragma unroll
-    for (int k = 0; k < kMaxPerLane; ++k) {
+    for (int k = 0; k < WMAX; ++k) {
         const int j = lane * per + k;
         loc[k] = (k < per && j < nw) ? __fadd_rn(w[j + 1], 1e-5f) : 0.0f;
         lsum += loc[k];
@@ -294,7 +301,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_fine_kernel(
     // last bit of neighbouring cdf entries, so the rounding of the scan matters).
     double lp = 0.0;
 #pragma unroll
-    for (int k = 0; k < kMaxPerLane; ++k) {
+    for (int k = 0; k < WMAX; ++k) {
         loc[k] = __fdiv_rn(loc[k], total);
         lp += (double)loc[k];
     }
@@ -307,7 +314,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_fine_kernel(
     double run = __shfl_up_sync(kFull, incl, 1);
     if (lane == 0) run = 0.0;
 #pragma unroll
-    for (int k = 0; k < kMaxPerLane; ++k) {
+    for (int k = 0; k < WMAX; ++k) {
         const int j = lane * per + k;
         if (k < per && j < nw) {
             run += (double)loc[k];
@@ -323,25 +330,45 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_fine_kernel(
     if (zc) for (int j = lane; j < S; j += 32) srt[j] = zc[j];
     for (int j = S + Ni + lane; j < P; j += 32) srt[j] = CUDART_INF_F;
     __syncwarp();
-    // inverse CDF
+    // inverse CDF: four independent binary searches per lane in flight (each step is a dependent shared-memory load)
     float m1 = 0.0f;
-    for (int k = lane; k < Ni; k += 32) {
-        const float u = u_in ? u_in[ray * Ni + k] : linspace01(k, Ni);
-        int lo = 0, hi = nb;                              // first index with cdf[idx] > u  (searchsorted right=True)
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+    const int n_steps = 32 - __clz(nb);                       // ceil(log2(nb + 1)): enough for a range of nb + 1 outcomes
+    constexpr int KS = 4;
+    for (int k0 = lane; k0 < Ni; k0 += 32 * KS) {
+        float u[KS];
+        int lo[KS], hi[KS];
+#pragma unroll
+        for (int q = 0; q < KS; ++q) {
+            const int k = k0 + 32 * q;
+            u[q] = k < Ni ? (u_in ? u_in[ray * Ni + k] : linspace01(k, Ni)) : 0.0f;
+            lo[q] = 0;
+            hi[q] = nb;                                       // first index with cdf[idx] > u  (searchsorted right=True)
         }
-        const int below = max(lo - 1, 0), above = min(lo, nb - 1);
-        const float c0 = cdf[below], c1 = cdf[above];
-        float den = __fsub_rn(c1, c0);
-        if (den < 1e-5f) den = 1.0f;
-        const float t = __fdiv_rn(__fsub_rn(u, c0), den);
-        const float b0 = bins[below], b1 = bins[above];
-        const float zs = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
-        srt[S + k] = zs;
-        if (z_samples_out) z_samples_out[ray * Ni + k] = zs;
-        m1 += zs;
+        for (int step = 0; step < n_steps; ++step) {
+#pragma unroll
+            for (int q = 0; q < KS; ++q) {
+                if (lo[q] < hi[q]) {
+                    const int mid = (lo[q] + hi[q]) >> 1;
+                    if (cdf[mid] <= u[q]) lo[q] = mid + 1; else hi[q] = mid;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < KS; ++q) {
+            const int k = k0 + 32 * q;
+            if (k < Ni) {
+                const int below = max(lo[q] - 1, 0), above = min(lo[q], nb - 1);
+                const float c0 = cdf[below], c1 = cdf[above];
+                float den = __fsub_rn(c1, c0);
+                if (den < 1e-5f) den = 1.0f;
+                const float t = __fdiv_rn(__fsub_rn(u[q], c0), den);
+                const float b0 = bins[below], b1 = bins[above];
+                const float zs = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+                srt[S + k] = zs;
+                if (z_samples_out) z_samples_out[ray * Ni + k] = zs;
+                m1 += zs;
+            }
+        }
     }
     // z_std = std(z_samples, unbiased=False)
     const float mean = warp_sum(m1) / (float)Ni;
@@ -584,8 +611,18 @@ extern "C" int nerfq_composite_fwd(const float* raw, const float* z, const float
                                    cudaStream_t stream) {
     if (n_rays == 0) return 0;
     if (!raw || !z || !rays || !rgb || !disp || !acc || S < 1 || S > 32 * kMaxPerLane || n_rays < 0) return -1;
-    composite_fwd_kernel<<<(unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock), 32 * kWarpsPerBlock, 0, stream>>>(
-        raw, z, rays, noise, white_bkgd, n_rays, S, rgb, disp, acc, depth, weights);
+    const unsigned grid = (unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    auto launch = [&](auto kernel) { kernel<<<grid, 32 * kWarpsPerBlock, 0, stream>>>(raw, z, rays, noise, white_bkgd, n_rays, S, rgb, disp, acc, depth, weights); };
+    switch ((S + 31) / 32) {            // samples per lane
+        case 1: launch(composite_fwd_kernel<1>); break;
+        case 2: launch(composite_fwd_kernel<2>); break;
+        case 3: launch(composite_fwd_kernel<3>); break;
+        case 4: launch(composite_fwd_kernel<4>); break;
+        case 5: launch(composite_fwd_kernel<5>); break;
+        case 6: launch(composite_fwd_kernel<6>); break;
+        case 7: launch(composite_fwd_kernel<7>); break;
+        default: launch(composite_fwd_kernel<8>); break;
+    }
     return launch_ok();
 }
 
@@ -593,8 +630,18 @@ extern "C" int nerfq_composite_bwd(const float* raw, const float* z, const float
                                    const float* d_rgb, long long n_rays, int S, float* d_raw, cudaStream_t stream) {
     if (n_rays == 0) return 0;
     if (!raw || !z || !rays || !d_rgb || !d_raw || S < 1 || S > 32 * kMaxPerLane || n_rays < 0) return -1;
-    composite_bwd_kernel<<<(unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock), 32 * kWarpsPerBlock, 0, stream>>>(
-        raw, z, rays, noise, white_bkgd, d_rgb, n_rays, S, d_raw);
+    const unsigned grid = (unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    auto launch = [&](auto kernel) { kernel<<<grid, 32 * kWarpsPerBlock, 0, stream>>>(raw, z, rays, noise, white_bkgd, d_rgb, n_rays, S, d_raw); };
+    switch ((S + 31) / 32) {            // samples per lane
+        case 1: launch(composite_bwd_kernel<1>); break;
+        case 2: launch(composite_bwd_kernel<2>); break;
+        case 3: launch(composite_bwd_kernel<3>); break;
+        case 4: launch(composite_bwd_kernel<4>); break;
+        case 5: launch(composite_bwd_kernel<5>); break;
+        case 6: launch(composite_bwd_kernel<6>); break;
+        case 7: launch(composite_bwd_kernel<7>); break;
+        default: launch(composite_bwd_kernel<8>); break;
+    }
     return launch_ok();
 }
 
@@ -617,11 +664,19 @@ extern "C" int nerfq_sample_fine(const float* z_coarse, const float* bins, const
         if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kernel<<<grid, 32 * kWarpsPerBlock, smem, stream>>>(z_coarse, bins, weights, u, n_rays, S, Ni, P, z_out, z_std, z_samples);
     };
+    const int wper = (S - 2 + 31) / 32;
+    auto pick = [&](auto per_c) {
+        constexpr int kPer = decltype(per_c)::value;
+        if (wper <= 1) launch(sample_fine_kernel<kPer, 1>);
+        else if (wper <= 2) launch(sample_fine_kernel<kPer, 2>);
+        else if (wper <= 4) launch(sample_fine_kernel<kPer, 4>);
+        else launch(sample_fine_kernel<kPer, 8>);
+    };
     switch (P / 32) {
-        case 1: launch(sample_fine_kernel<1>); break;
-        case 2: launch(sample_fine_kernel<2>); break;
-        case 4: launch(sample_fine_kernel<4>); break;
-        default: launch(sample_fine_kernel<8>); break;
+        case 1: pick(std::integral_constant<int, 1>{}); break;
+        case 2: pick(std::integral_constant<int, 2>{}); break;
+        case 4: pick(std::integral_constant<int, 4>{}); break;
+        default: pick(std::integral_constant<int, 8>{}); break;
     }
     return launch_ok();
 }
