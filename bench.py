@@ -625,21 +625,25 @@ def dp_checks(dev, rank, world, timed, rays_d, t_d, step_kw):
         codec.quantize_model(w, QP)
         return w
     out = {}
-    # (a) exposed time
+    # (a) exposed time: the same captured step with the fused peer-memory finalize (default when the ranks can map each
+    # other's memory), with one NCCL all-reduce, and with the collective switched off
     res = {}
-    for dp in (True, False):
-        D.enable_data_parallel(dp)
+    for name, kw_dp in (("peer", dict(enabled=True)), ("nccl", dict(enabled=True, peer=False)), ("off", dict(enabled=False))):
+        D.enable_data_parallel(**kw_dp)
+        if name == "peer":
+            out["collective"] = R.DATA_PARALLEL["collective"]
         st = lsa.LSAStep(make(), RAYS_PER_GPU, requantize=None, **step_kw)
         st.capture()
-        res[dp] = timed(lambda: st(rays_d, t_d), 20, 5)
+        res[name] = timed(lambda: st(rays_d, t_d), 20, 5)
         st.graph = None
-    # (b) the collective alone: one int64[2, 2440] all-reduce (what a step issues)
-    D.enable_data_parallel(True)
+    # (b) the NCCL collective alone: one int64[2, 2440] all-reduce
     fix = torch.zeros((2, 2440), dtype=torch.int64, device=dev)
     ms_ar = timed(lambda: dist.all_reduce(fix), 50, 10)
-    out["allreduce"] = {"ms_step_with": res[True], "ms_step_without": res[False], "ms_exposed": res[True] - res[False],
-                        "ms_allreduce_alone": ms_ar, "bytes": 2 * 2440 * 8,
-                        "note": "one NCCL int64 all-reduce of both networks' fixed-point sums after the last backward kernel; exposed"}
+    D.enable_data_parallel(True)
+    out["allreduce"] = {"collective": out["collective"], "ms_step_with": res["peer"], "ms_step_with_nccl": res["nccl"], "ms_step_without": res["off"],
+                        "ms_exposed": res["peer"] - res["off"], "ms_exposed_nccl": res["nccl"] - res["off"],
+                        "ms_nccl_allreduce_alone": ms_ar, "bytes": 2 * 2440 * 8,
+                        "note": "ms_exposed: captured LSA step with the collective minus the same step without it"}
     # (c) bit parity
     n = 1024
     batches = [synth_batch(n, 2 + 10 * r) for r in range(world)]

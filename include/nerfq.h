@@ -110,6 +110,19 @@ int nerfq_mlp_backward_partial(const void* packed, const float* d_raw, const flo
                                long long* grad_fix, int max_ctas, nerfq_stream_t stream);
 int nerfq_mlp_backward_finalize(const void* packed, long long* grad_fix, float* d_scale, nerfq_stream_t stream);
 
+/* The same with the all-reduce fused in, for the ranks of ONE node (NVLink / NVSwitch peer access): every rank maps a
+ * region of nerfq_dp_peer_bytes() bytes of every other rank (e.g. torch.distributed._symmetric_memory, cuMem + fabric/fd
+ * handles), zero-initialised before first use; `peers` is a DEVICE array of `world` pointers to these regions in rank
+ * order.  One launch per step on every rank replaces {all-reduce, finalize(coarse), finalize(fine)}: it publishes
+ * grad_fix2 (DEVICE int64[2][nerfq_mlp_grad_fix_bytes()/8]: coarse, fine; left zeroed) in the rank's own region, exchanges
+ * epoch flags with all peers, reads every rank's sums over the interconnect and accumulates the converted result into
+ * d_scale2 (DEVICE float[2][2436]).  `epoch` is a DEVICE counter owned by the rank (zero at start, advanced by the kernel,
+ * so the launch can sit in a CUDA graph).  Every rank must issue the same sequence of calls; a peer that never arrives
+ * makes the kernel trap after a bounded wait.  packed_fine == NULL: only the coarse network carries sums. */
+unsigned long long nerfq_dp_peer_bytes(void);
+int nerfq_mlp_backward_finalize_peers(const void* packed_coarse, const void* packed_fine, long long* grad_fix2, void* const* peers,
+                                      int world, int rank, unsigned int* epoch, float* d_scale2, nerfq_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Ray-side kernels
  * ---------------------------------------------------------------------------------------------- */

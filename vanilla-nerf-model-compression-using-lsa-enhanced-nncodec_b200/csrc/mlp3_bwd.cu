@@ -20,6 +20,7 @@
 // which keeps fp16's 11-bit significand for the operands without its range problem.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <stdio.h>
 
 #include "mlp3_common.cuh"
 
@@ -386,6 +387,100 @@ __global__ void mlp3_backward_finalize_kernel(const uint8_t* packed, long long* 
     }
 }
 
+// ---- data-parallel finalize over peer memory ---------------------------------------------------------------------
+// The all-reduce of the fixed-point sums fused into the finalize step: every rank copies its sums into a staging area
+// that all ranks of the node map (symmetric memory over NVLink / NVSwitch), raises a flag in every peer's pad, waits for
+// every peer's flag, and then reads ALL ranks' staged sums directly and adds them up.  Integer addition: every rank gets
+// the same bits whatever the order, and the same bits as one rank on the concatenated batch.  One kernel, one block;
+// replaces {NCCL all-reduce (0.032 ms at N = 8 plus two kernel boundaries: 0.069 ms exposed) ; finalize ; finalize}.
+//
+// Peer region layout (nerfq_dp_peer_bytes(), zero-initialised once, before the ranks first meet):
+//   long long stage[2][2][2440]   [epoch parity][network][channel]     unsigned pad[64] at kPeerPadOff: pad[r] = last epoch
+//                                                                       rank r has published
+// Reuse: stage[e & 1] is rewritten by its owner at epoch e + 2, i.e. after the owner has seen every peer's flag of epoch
+// e + 1, which a peer raises only after it finished reading epoch e.  Waits are bounded (a dead peer traps, not hangs).
+constexpr int kPeerNetElems = 2440;
+constexpr size_t kPeerPadOff = (size_t)2 * 2 * kPeerNetElems * sizeof(long long);
+constexpr size_t kPeerBytes = kPeerPadOff + 64 * sizeof(unsigned);
+
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ long long ld_relaxed_sys_s64(const long long* p) {      // system-coherent: never served by a stale L1 line
+    long long v;
+    asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(1024) mlp3_backward_finalize_peers_kernel(const uint8_t* packed0, const uint8_t* packed1,
+                                                                             long long* __restrict__ fix, uint8_t* const* __restrict__ peers,
+                                                                             int world, int rank, unsigned* __restrict__ epoch_p,
+                                                                             float* __restrict__ d_scale) {
+    const unsigned e = *epoch_p + 1u;                       // epochs start at 1; the pads start at 0
+    const int par = (int)(e & 1u);
+    const int n = 2 * kPeerNetElems;
+    long long* stage = reinterpret_cast<long long*>(peers[rank]) + par * n;
+    // (0) publish this rank's sums; the accumulators are left zeroed for the next backward
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        stage[i] = fix[i];
+        fix[i] = 0;
+    }
+    __threadfence_system();
+    __syncthreads();
+    // (1) raise this rank's flag in every peer's pad, then wait for every peer's flag in ours
+    if ((int)threadIdx.x < world) {
+        st_release_sys_u32(reinterpret_cast<unsigned*>(peers[threadIdx.x] + kPeerPadOff) + rank, e);
+        const unsigned* mine = reinterpret_cast<const unsigned*>(peers[rank] + kPeerPadOff) + threadIdx.x;
+        unsigned spins = 0;
+        while ((int)(ld_acquire_sys_u32(mine) - e) < 0) {
+            if (++spins > (1u << 26)) {
+                printf("nerfq: data-parallel finalize: rank %d gave up waiting for rank %d at epoch %u\n", rank, (int)threadIdx.x, e);
+                __trap();
+            }
+        }
+    }
+    __syncthreads();
+    // (2) add up all ranks' staged sums and convert.  The reads cross NVLink (~2 us each): a thread keeps 4 ranks x 5
+    // elements = 20 of them in flight, so N = 8 costs two round trips, not forty.
+    constexpr int kPerThread = (2 * kPeerNetElems + 1023) / 1024;       // 5
+    long long q[kPerThread];
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k) q[k] = 0;
+    for (int r0 = 0; r0 < world; r0 += 4) {
+        long long v[4][kPerThread];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const long long* src = reinterpret_cast<const long long*>(peers[min(r0 + rr, world - 1)]) + par * n;
+#pragma unroll
+            for (int k = 0; k < kPerThread; ++k) {
+                const int i = (int)threadIdx.x + 1024 * k;
+                v[rr][k] = (r0 + rr < world && i < n) ? ld_relaxed_sys_s64(src + i) : 0;
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+            for (int k = 0; k < kPerThread; ++k) q[k] += v[rr][k];
+    }
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k) {
+        const int i = (int)threadIdx.x + 1024 * k;
+        if (i >= n) continue;
+        const int net = i / kPeerNetElems, c = i - net * kPeerNetElems;
+        if (c < kNumChannels && q[k] != 0) {
+            const float sc = reinterpret_cast<const float*>((net ? packed1 : packed0) + kOffScale)[c];
+            if (sc != 0.0f) d_scale[net * kNumChannels + c] += (float)((double)q[k] * (1.0 / (double)(1ull << kGradFixShift))) / sc;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *epoch_p = e;
+}
+
 }  // namespace nerfq
 
 static unsigned long long* g_trace3b = nullptr;
@@ -422,6 +517,17 @@ extern "C" int nerfq_mlp_backward_finalize(const void* packed, long long* grad_f
     using namespace nerfq;
     if (!packed || !grad_fix || !d_scale) return -1;
     mlp3_backward_finalize_kernel<<<(kNumChannels + 255) / 256, 256, 0, stream>>>((const uint8_t*)packed, grad_fix, d_scale);
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+extern "C" unsigned long long nerfq_dp_peer_bytes(void) { return nerfq::kPeerBytes; }
+
+extern "C" int nerfq_mlp_backward_finalize_peers(const void* packed_coarse, const void* packed_fine, long long* grad_fix2, void* const* peers,
+                                                  int world, int rank, unsigned int* epoch, float* d_scale2, cudaStream_t stream) {
+    using namespace nerfq;
+    if (!packed_coarse || !grad_fix2 || !peers || !epoch || !d_scale2 || world < 1 || world > 64 || rank < 0 || rank >= world) return -1;
+    mlp3_backward_finalize_peers_kernel<<<1, 1024, 0, stream>>>((const uint8_t*)packed_coarse, (const uint8_t*)(packed_fine ? packed_fine : packed_coarse),
+                                                               grad_fix2, (uint8_t* const*)peers, world, rank, epoch, d_scale2);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 

@@ -26,12 +26,63 @@ def allreduce_fixed(fix: torch.Tensor, group=None) -> torch.Tensor:
     return fix
 
 
-def enable_data_parallel(enabled: bool = True, group=None):
-    """Switch the renderer's backward (render._backward_pipeline, used by autograd and by lsa.LSAStep) to data parallel."""
+class PeerState:
+    """Symmetric-memory region for the fused data-parallel finalize (include/nerfq.h, nerfq_mlp_backward_finalize_peers):
+    every rank of the node maps every other rank's staging area + flag pad.  Built once per (device, group) and kept."""
+    _cache = {}
+
+    def __init__(self, dev, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import ops
+        nbytes = ops.dp_peer_bytes()
+        self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.buf.zero_()
+        torch.cuda.synchronize(dev)
+        pg = group if group is not None else dist.group.WORLD
+        try:
+            self.handle = symm_mem.rendezvous(self.buf, pg)
+        except TypeError:
+            self.handle = symm_mem.rendezvous(self.buf, pg.group_name)
+        self.world, self.rank = int(self.handle.world_size), int(self.handle.rank)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        assert len(ptrs) == self.world and ptrs[self.rank] == self.buf.data_ptr()
+        self.ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)           # DEVICE array of the peers' base pointers
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)            # nobody raises a flag in a pad that is not zeroed yet
+
+    @classmethod
+    def get(cls, dev, group):
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(), id(group))
+        if key not in cls._cache:
+            cls._cache[key] = cls(dev, group)
+        return cls._cache[key]
+
+
+def enable_data_parallel(enabled: bool = True, group=None, peer: Optional[bool] = None):
+    """Switch the renderer's backward (render._backward_pipeline, used by autograd and by lsa.LSAStep) to data parallel.
+
+    peer: None (default) -- use the fused peer-memory finalize when the ranks of the group can map each other's memory
+    (torch symmetric memory: one node, NVLink / NVSwitch), otherwise one NCCL int64 all-reduce per step; True -- require it;
+    False -- NCCL.  Environment NERFQ_DP_PEER=0 forces NCCL.  render.DATA_PARALLEL['collective'] names what is in use."""
+    import os
+    import sys
     from . import render
-    render.DATA_PARALLEL["enabled"] = bool(enabled) and dist.is_initialized() and dist.get_world_size(group) > 1
+    on = bool(enabled) and dist.is_initialized() and dist.get_world_size(group) > 1
+    render.DATA_PARALLEL["enabled"] = on
     render.DATA_PARALLEL["group"] = group
-    return render.DATA_PARALLEL["enabled"]
+    render.DATA_PARALLEL["peer"] = None
+    render.DATA_PARALLEL["collective"] = "nccl all_reduce (int64)" if on else None
+    if on and peer is not False and os.environ.get("NERFQ_DP_PEER", "1") != "0" and torch.cuda.is_available():
+        try:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            render.DATA_PARALLEL["peer"] = PeerState.get(dev, group)
+            render.DATA_PARALLEL["collective"] = "peer-memory finalize kernel (symmetric memory)"
+        except Exception as ex:  # noqa: BLE001
+            if peer:
+                raise
+            sys.stderr.write(f"nerfq: symmetric memory is not available ({type(ex).__name__}: {str(ex)[:200]}); data-parallel gradients use NCCL\n")
+    return on
 
 
 def render_view_sharded(H: int, W: int, K, c2w, render_kwargs: dict, chunk: int = 32768, ndc: bool = False, near: float = 2.0,

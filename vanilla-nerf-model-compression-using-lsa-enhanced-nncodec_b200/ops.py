@@ -42,6 +42,8 @@ _PROTOS = {
     "nerfq_mlp_backward_partial": (_c.c_int, [_c.c_void_p] * 4 + [_c.c_longlong, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "nerfq_mlp_backward_finalize": (_c.c_int, [_c.c_void_p] * 4),
     "nerfq_mlp_grad_fix_bytes": (_c.c_ulonglong, []),
+    "nerfq_dp_peer_bytes": (_c.c_ulonglong, []),
+    "nerfq_mlp_backward_finalize_peers": (_c.c_int, [_c.c_void_p] * 4 + [_c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "nerfq_render_rays_workspace_bytes": (_c.c_ulonglong, [_c.c_longlong, _c.c_int, _c.c_int]),
     "nerfq_render_rays_fwd": (_c.c_int, [_c.c_void_p] * 3 + [_c.c_longlong, _c.c_int, _c.c_int, _c.c_int, _c.c_int] + [_c.c_void_p] * 8 +
                               [_c.c_int, _c.c_void_p]),
@@ -265,6 +267,22 @@ def mlp_backward_finalize(net: PackedNet, grad_fix: torch.Tensor, d_scale: torch
     assert d_scale.is_cuda and d_scale.dtype == torch.float32 and d_scale.is_contiguous() and d_scale.numel() == 2436
     _lib.check(L().nerfq_mlp_backward_finalize(net.ptr, grad_fix.data_ptr(), d_scale.data_ptr(), _stream()), "nerfq_mlp_backward_finalize")
     return d_scale
+
+
+def dp_peer_bytes() -> int:
+    return int(L().nerfq_dp_peer_bytes())
+
+
+def mlp_backward_finalize_peers(net0: PackedNet, net1: Optional[PackedNet], grad_fix2: torch.Tensor, peers_dev: int, world: int, rank: int,
+                                epoch: torch.Tensor, d_scale2: torch.Tensor) -> torch.Tensor:
+    """Data-parallel finalize with the all-reduce fused in (nerfq_mlp_backward_finalize_peers): grad_fix2 int64 [2, 2440] (coarse,
+    fine) is published to the peers, all ranks' sums are added up and d_scale2 float32 [2, 2436] accumulates the gradients."""
+    assert grad_fix2.dtype == torch.int64 and grad_fix2.is_contiguous() and grad_fix2.numel() == 2 * grad_fix_elems()
+    assert d_scale2.dtype == torch.float32 and d_scale2.is_contiguous() and d_scale2.numel() == 2 * 2436
+    assert epoch.dtype == torch.int32 and epoch.is_cuda
+    _lib.check(L().nerfq_mlp_backward_finalize_peers(net0.ptr, net1.ptr if net1 is not None else None, grad_fix2.data_ptr(), peers_dev, int(world),
+                                                     int(rank), epoch.data_ptr(), d_scale2.data_ptr(), _stream()), "nerfq_mlp_backward_finalize_peers")
+    return d_scale2
 
 
 # ---- one-call forward render, image output, batch selection ---------------------------------------------------

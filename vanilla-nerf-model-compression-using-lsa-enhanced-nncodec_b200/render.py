@@ -30,7 +30,7 @@ to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)
 
 TUNING = {"max_ctas": 0}      # kernel scheduling knob (bench/profiling)
 # data-parallel LSA tuning: all-reduce the scale gradients over torch.distributed (group None = the default group)
-DATA_PARALLEL = {"enabled": False, "group": None}
+DATA_PARALLEL = {"enabled": False, "group": None, "peer": None, "collective": None}
 
 
 class _FusedQuery:
@@ -195,6 +195,14 @@ def _backward_pipeline(cfg: _Cfg, st: dict, d_rgb1, d_rgb0, g_out: Optional[torc
         ops.mlp_backward_partial(pn, d_raw, raw, save, dps.fix[slot], max_ctas=mc)
         if slot not in slots:
             slots.append(slot)
+    peer = DATA_PARALLEL.get("peer")
+    if peer is not None and g_out.is_contiguous() and g_out.shape[0] == 2:
+        # all-reduce fused into the finalize: one kernel publishes this rank's sums, meets the peers and adds up everybody's
+        # sums read straight from their memory (include/nerfq.h: nerfq_mlp_backward_finalize_peers)
+        by_slot = {slot: pn for pn, _, _, _, _, _, slot in passes}
+        ops.mlp_backward_finalize_peers(by_slot.get(0, by_slot.get(1)), by_slot.get(1), dps.fix, int(peer.ptrs.data_ptr()), peer.world, peer.rank,
+                                        peer.epoch, g_out)
+        return g0, g1
     # ONE all-reduce for both networks (39 KB of int64).  Overlapping the fine network's all-reduce with the coarse
     # network's backward on a side stream was tried in round 2 and bought nothing: the persistent backward kernel holds
     # every SM, so NCCL's kernel only got an SM when that kernel ended, and the two all-reduces ran back to back at the
