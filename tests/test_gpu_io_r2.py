@@ -163,3 +163,33 @@ def test_load_levels_matches_apply_lsa(dev):
         a = R.render(4, 4, None, rays=rays, near=2.0, far=6.0, **kw_a)
         b = R.render(4, 4, None, rays=rays, near=2.0, far=6.0, **kw_b)
     assert maxerr(a[0], b[0]) < GATE and maxerr(a[2], b[2]) < GATE
+
+
+def test_peer_finalize_single_rank_equals_the_plain_finalize(dev):
+    """nerfq_mlp_backward_finalize_peers with a world of one rank (its own region is the only peer) must produce exactly what
+    the two plain finalize launches produce, leave the accumulators zeroed, and keep doing so across epochs (the staging
+    area alternates with the epoch parity).  The multi-rank behaviour -- bit-identical to one GPU on the concatenated
+    batch -- is asserted on hardware by bench.py --gpus N (`dp_parity`) and profiles/dp_parity_check.py."""
+    from nerfq_b200 import ops
+    from tests.gpu_util import golden_wrapper
+    w, _ = golden_wrapper(dev, True)
+    pn0, pn1 = w.model.packed_net(), w.model_fine.packed_net()
+    pn0.set_scales(w.model.scale_tensors())
+    pn1.set_scales(w.model_fine.scale_tensors())
+    n = ops.grad_fix_elems()
+    region = torch.zeros(ops.dp_peer_bytes(), dtype=torch.uint8, device=dev)
+    peers = torch.tensor([region.data_ptr()], dtype=torch.int64, device=dev)
+    epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+    gen = torch.Generator().manual_seed(7)
+    for it in range(3):
+        fix = (torch.randint(-2**40, 2**40, (2, n), generator=gen, dtype=torch.int64)).to(dev)
+        fix[:, 2436:] = 0
+        ref = torch.zeros((2, 2436), device=dev)
+        f0, f1 = fix[0].clone(), fix[1].clone()
+        ops.mlp_backward_finalize(pn0, f0, ref[0])
+        ops.mlp_backward_finalize(pn1, f1, ref[1])
+        got = torch.zeros((2, 2436), device=dev)
+        ops.mlp_backward_finalize_peers(pn0, pn1, fix, int(peers.data_ptr()), 1, 0, epoch, got)
+        torch.cuda.synchronize()
+        assert torch.equal(got, ref) and float(ref.abs().max()) > 0
+        assert int(fix.abs().max()) == 0 and int(epoch.item()) == it + 1
