@@ -19,16 +19,21 @@ from .model import NeRF
 
 def _quantize_nets(nets, qp: int, qp_density: int, nonweight_qp: int):
     """One launch pair for every weight and bias of `nets`: levels out, parameters overwritten with level*delta."""
-    tensors, qps = [], []
+    tensors, qps, reuse = [], [], []
     for net in nets:
-        for layer in net.layers():
+        # a requantisation writes into the level tensors the network already holds (no new allocation: the python attributes
+        # and every captured graph keep referring to the same memory); the first quantisation allocates them
+        prev = net.quant_levels if (net.quant_levels is not None and net._quant_key is not None) else None
+        for i, layer in enumerate(net.layers()):
             tensors += [layer.weight.data, layer.bias.data]
             qps += [qp, nonweight_qp]
+            ok = prev is not None and prev[i].dtype == torch.int32 and prev[i].shape == layer.weight.shape and prev[i].is_contiguous()
+            reuse += [prev[i] if ok else None, None]
     for x in tensors:
         assert x.dtype == torch.float32 and x.is_contiguous()
     outs = []
     for i in range(0, len(tensors), 64):
-        lv, _ = ops.quantize_batch(tensors[i:i + 64], qps[i:i + 64], qp_density, reconstruct_in_place=True)
+        lv, _ = ops.quantize_batch(tensors[i:i + 64], qps[i:i + 64], qp_density, reconstruct_in_place=True, levels_out=reuse[i:i + 64])
         outs += lv
     step = ops.stepsize(qp, qp_density)
     res, k = [], 0

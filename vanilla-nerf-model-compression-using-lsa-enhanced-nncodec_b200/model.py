@@ -102,9 +102,22 @@ class NeRF(nn.Module):
         parameters hold right now.  They are the MLP kernels' operands for as long as the float weights stay untouched:
         any later load_state_dict / in-place update of a weight (a version-counter bump) drops them, and the renderer
         packs the float weights again -- so state_dict(), NeRF.forward and the fused path never disagree."""
+        # the same level tensors as before (a requantisation wrote new values into them, codec._quantize_nets): repack into the
+        # existing buffers instead of allocating new ones, so every holder of the packed network -- python attributes, and
+        # each CUDA graph that recorded a requantisation -- keeps seeing the one live copy
+        same = (levels is not None and self.quant_levels is not None and self._packed is not None and self._packed.is_int and
+                len(levels) == len(self.quant_levels) and all(a.data_ptr() == b.data_ptr() for a, b in zip(levels, self.quant_levels)))
         self.quant_levels, self.quant_steps = (list(levels), list(steps)) if levels is not None else (None, None)
         self._quant_key = self._weight_key() if levels is not None else None
-        self._packed = None
+        if same:
+            self._packed.repack(self.quant_levels, self.quant_steps, [l.bias.detach() for l in self.layers()])
+            self._packed_key = self._pack_key()
+        else:
+            self._packed = None
+
+    def _pack_key(self):
+        return tuple((l.weight.data_ptr(), l.weight._version, l.bias.data_ptr(), l.bias._version) for l in self.layers()) + \
+            (id(self.quant_levels),)
 
     def packed_net(self) -> packed.PackedNet:
         """Pack (or reuse) the frozen weights; biases and scales are refreshed by the caller."""
@@ -114,8 +127,7 @@ class NeRF(nn.Module):
         ls = self.layers()
         if self.quant_levels is not None and self._quant_key is not None and self._quant_key != self._weight_key():
             self.quant_levels = self.quant_steps = self._quant_key = None       # the float weights moved on: levels are stale
-        key = tuple((l.weight.data_ptr(), l.weight._version, l.bias.data_ptr(), l.bias._version) for l in ls) + \
-            (id(self.quant_levels),)
+        key = self._pack_key()
         if self._packed is None or key != self._packed_key:
             biases = [l.bias.detach() for l in ls]
             if self.quant_levels is not None:

@@ -92,7 +92,8 @@ def quantize_batch(tensors: Sequence[torch.Tensor], qps: Sequence[int], qp_densi
     dev = tensors[0].device
     for x in tensors:
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
-    lv = list(levels_out) if levels_out is not None else [torch.empty(x.shape, dtype=torch.int32, device=dev) for x in tensors]
+    lv = [levels_out[i] if (levels_out is not None and levels_out[i] is not None) else torch.empty(x.shape, dtype=torch.int32, device=dev)
+          for i, x in enumerate(tensors)]
     ws = torch.empty(2 * t, dtype=torch.int32, device=dev)
     vp = _c.c_void_p * t
     w_arr = vp(*[x.data_ptr() for x in tensors])

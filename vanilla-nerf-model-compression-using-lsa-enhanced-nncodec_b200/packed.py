@@ -68,18 +68,31 @@ class PackedNet:
             ws.append(w.contiguous())
         self.device = dev
         self.buf = torch.empty(int(L.nerfq_packed_net_bytes()), dtype=torch.uint8, device=dev)
-        ptrs = (ctypes.c_void_p * 12)(*[w.data_ptr() for w in ws])
-        dl = (ctypes.c_float * 12)(*[float(d) for d in deltas])
-        _lib.check(L.nerfq_pack_net(self.buf.data_ptr(), ptrs, dl, int(is_int), _stream()), "nerfq_pack_net")
-        self._keep = ws
         self.is_int = is_int
         self._max_abs = torch.empty(12, dtype=torch.float32, device=dev)
+        self.bias_flat = torch.empty(NUM_CHANNELS, dtype=torch.float32, device=dev)
+        self.scale_flat = None
+        self._pack(ws, deltas, biases)
+        self.set_scales(scales)
+
+    def _pack(self, ws, deltas, biases):
+        L = _lib.lib()
+        ptrs = (ctypes.c_void_p * 12)(*[w.data_ptr() for w in ws])
+        dl = (ctypes.c_float * 12)(*[float(d) for d in deltas])
+        _lib.check(L.nerfq_pack_net(self.buf.data_ptr(), ptrs, dl, int(self.is_int), _stream()), "nerfq_pack_net")
+        self._keep = ws
         _lib.check(L.nerfq_pack_status(self.buf.data_ptr(), self._max_abs.data_ptr(), _stream()), "nerfq_pack_status")
         self._range_checked = False
         if not torch.cuda.is_current_stream_capturing():
             self.check_range()
-        self.bias_flat = flatten_channels(biases).to(dev)
-        self.set_scales(scales)
+        self.bias_flat.copy_(flatten_channels(biases))
+
+    def repack(self, weights: Sequence[torch.Tensor], deltas: Sequence[float], biases: Sequence[torch.Tensor]):
+        """Pack new values of the same kind (int32 levels / float32) into the SAME buffers.  Like a fresh PackedNet the
+        result needs set_scales() before it is used (nerfq_set_scale_bias must follow every nerfq_pack_net); every caller in
+        this package goes through render._refresh, which does that."""
+        assert len(weights) == 12 and all(w.dtype == (torch.int32 if self.is_int else torch.float32) and w.is_contiguous() for w in weights)
+        self._pack(list(weights), deltas, biases)
 
     def max_abs_per_layer(self):
         """max |level| (or |weight|) of the 12 layers as packed (synchronises)."""
