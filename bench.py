@@ -31,6 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 RAYS_PER_GPU = 4096
+SETTLE_S = 0.5          # idle time before every timed region (see run_cuda.timed)
 N_SAMPLES, N_IMPORTANCE = 64, 128
 QP, QP_DENSITY, NONWEIGHT_QP = -20, 2, -75
 FLOP_PER_POINT_FWD = 2 * 593408
@@ -238,6 +239,11 @@ def run_cuda(args):
             step_main.graph = step_noq.graph = None
 
     def timed(fn, steps, warmup):
+        # These boxes run power-capped and the SM clock sags within a few hundred ms of load: identical replays went from 2.75
+        # to 2.93 ms inside one process (profiles/r02_e2e_probe.log), so whatever was timed first looked 3-8 % faster than
+        # what came next.  Every timed region therefore starts from the same state: device drained, SETTLE_S idle, warm-up.
+        torch.cuda.synchronize()
+        time.sleep(SETTLE_S)
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
@@ -260,12 +266,26 @@ def run_cuda(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # (2) end to end through the public API with host buffers: H2D of rays+target and D2H of the loss, every step.
+    # The loop a user who logs the loss every iteration writes (LSAStep.step_async): the loss of step i is read right after
+    # step i+1 has been enqueued, so the host's launch work overlaps the GPU's previous step.  `e2e_sync` is the same with
+    # a blocking read of each step's loss before the next step is enqueued (what `loss.item()` in the reference's loop does).
+    pending = [None]
+
+    def e2e_step():
+        nxt = step_main.step_async(rays_h, t_h)              # pinned host rays + target in
+        if pending[0] is not None:
+            pending[0].result()                               # loss of the previous step out (4 bytes D2H per step)
+        pending[0] = nxt
+
+    def e2e_sync_step():
+        return float(step_main(rays_h, t_h).cpu())
+
     # (1) device-resident inputs
     ms_step = timed(lambda: step_main(rays_d, t_d), args.steps, args.warmup)
-    # (2) end to end through the public API with host buffers: H2D of rays+target, D2H of the loss, every step
-    def e2e_step():
-        return float(step_main(rays_h, t_h).cpu())          # pinned host rays + target in, loss out, every step
     ms_e2e = timed(e2e_step, args.steps, min(args.warmup, 3))
+    pending[0].result()
+    ms_e2e_sync = timed(e2e_sync_step, args.steps, min(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
     ms_norequant = timed(lambda: step_noq(rays_d, t_d), args.steps, 3)
 
@@ -336,7 +356,11 @@ def run_cuda(args):
                            "parallelism": f"dp{world}" if world > 1 else "single",
                            "l2": "per-step working set (saved activations 5.1 GB/GPU) exceeds the 126 MB L2; no explicit flush"},
                 "e2e": {"value": world * RAYS_PER_GPU / (ms_e2e * 1e-3), "unit": "rays/s",
-                        "h2d_bytes_per_step": int(rays_h.numel() * 4 + t_h.numel() * 4), "d2h_bytes_per_step": 4},
+                        "h2d_bytes_per_step": int(rays_h.numel() * 4 + t_h.numel() * 4), "d2h_bytes_per_step": 4,
+                        "note": "LSAStep.step_async: every step copies its batch from pinned host memory and its loss back; the loss of "
+                                "step i is read after step i+1 has been enqueued (one step of pipelining)"},
+                "e2e_sync": {"value": world * RAYS_PER_GPU / (ms_e2e_sync * 1e-3), "unit": "rays/s",
+                             "note": "blocking read of every step's loss before the next step is enqueued"},
                 "clocks": clocks}
         # launches of OUR kernels per step: pack_rays 1, per network pass: set_scale_bias 1 + mlp_fwd 1 + composite_fwd 1,
         # coarse_depths 1, sample_fine 1, mse_grad 0 (torch), bwd: 2 x (composite_bwd 1 + mlp_bwd 1 + finalize 1);
@@ -426,6 +450,8 @@ def _dist_setup():
 def _timed_region(world, dev, fn, steps, warmup):
     """W warm-up calls, then `steps` calls between barrier + synchronize, CUDA events, max over ranks -> ms per call."""
     import torch.distributed as dist
+    torch.cuda.synchronize()
+    time.sleep(SETTLE_S)                     # same starting state for every timed region (see run_cuda.timed)
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()

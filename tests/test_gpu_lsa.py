@@ -123,3 +123,34 @@ def test_lsa_step_graph_replay_matches_eager(dev):
             assert torch.equal(a, b)
         for a, b in zip(q0, q1):
             assert torch.equal(a, b)
+
+
+def test_step_async_returns_each_iterations_own_loss(dev):
+    """LSAStep.step_async: results read one iteration late (the pipelined logging loop) are, iteration by iteration, the
+    values the blocking loop reads, for the eager path and for the captured graph."""
+    import copy
+    from nerfq_b200 import codec, lsa, model as nmodel
+    torch.manual_seed(4)
+    base = nmodel.LSA(nmodel.NeRFWrapper()).add_lsa_params().to(dev)
+    codec.quantize_model(base, -20)
+    r = synth_rays(256, 9)
+    rays = torch.stack([r[:, :3], r[:, 3:6]], 0).contiguous().pin_memory()
+    target = torch.rand(256, 3, generator=torch.Generator().manual_seed(10)).pin_memory()
+    for graphed in (False, True):
+        out = []
+        for mode in ("sync", "async"):
+            step = lsa.LSAStep(copy.deepcopy(base), 256, lr=1e-3, perturb=0.0, white_bkgd=True)
+            if graphed:
+                step.capture(warmup=0)
+            if mode == "sync":
+                out.append([float(step(rays, target).cpu()) for _ in range(4)])
+            else:
+                got, pending = [], None
+                for _ in range(4):
+                    nxt = step.step_async(rays, target)
+                    if pending is not None:
+                        got.append(pending.result())
+                    pending = nxt
+                got.append(pending.result())
+                out.append(got)
+        assert out[0] == out[1] and out[0][0] != out[0][3], out
