@@ -45,6 +45,9 @@ static_assert(kS3BwdMax + 32 <= kS3Misc, "backward scratch must fit the encoding
 #ifndef NERFQ_BWD_PREFETCH
 #define NERFQ_BWD_PREFETCH 1
 #endif
+#ifndef NERFQ_BWD_PF_DIST
+#define NERFQ_BWD_PF_DIST 2       // how many jobs ahead a job's slice of saved activations is requested into L2
+#endif
 // the 64 bytes (L2 fill granularity) around p into L2
 __device__ __forceinline__ void prefetch_l2_line(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p) : "memory");
@@ -190,9 +193,8 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 rw = *reinterpret_cast<const float4*>(prm.raw + 4 * gidx);
             }
             if (it == 0) {         // later groups: prefetched by the previous group's last jobs
-                prefetch_seq(g, 0);
-                prefetch_seq(g, 1);
-                prefetch_seq(g, 2);
+#pragma unroll
+                for (int v = 0; v <= NERFQ_BWD_PF_DIST; ++v) prefetch_seq(g, v);
             }
             const uint32_t slot_max = max_a + 4 * (it & 1);
             if (le < 4) {
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 // Each consumed slot is refilled with the chunk two ahead; chunks 2 and 3 free the slots for the next job.
                 const Job3 jn = prm.prog.job[j + 1 < kBwd3Jobs ? j + 1 : j];
                 const uint8_t* hrow_next = saved_row(gj, jn.slot, ((jn.flags & JB_HI_HALF) ? 128u : 0u) + cl);
-                if (j + 3 <= kBwd3Jobs) prefetch_seq(gj, j + 3);            // the job after next, into L2 (one line per thread)
+                if (j + 1 + NERFQ_BWD_PF_DIST <= kBwd3Jobs) prefetch_seq(gj, j + 1 + NERFQ_BWD_PF_DIST);      // NERFQ_BWD_PF_DIST jobs ahead, into L2 (one line per thread)
                 unsigned long long tj0 = 0;
                 if (tracing) tj0 = clock64();
                 if (hi) { mbar_wait_acc(bar(kB3AccReady + 2 * team + 1), ph_acc1); ph_acc1 ^= 1; }
@@ -356,9 +358,8 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 if (tracing) t_job += clock64() - tj0;
             }
             if (g + stride < prm.n_groups) {
-                prefetch_seq(g + stride, 0);
-                prefetch_seq(g + stride, 1);
-                prefetch_seq(g + stride, 2);
+#pragma unroll
+                for (int v = 0; v <= NERFQ_BWD_PF_DIST; ++v) prefetch_seq(g + stride, v);
             }
         }
         if (tracing && prm.dbg) {
