@@ -212,3 +212,30 @@ def test_stale_levels_are_dropped_when_weights_change(dev):
         _, kwo = R.create_nerf(other, white_bkgd=True)
         c = R.render(4, 4, None, rays=rays, near=2.0, far=6.0, **kwo)[0]
     assert torch.equal(b, c) and not torch.equal(a, b)
+
+
+@pytest.mark.parametrize("model", ["golden", "trained_spread"])
+def test_test_view_psnr_within_gate(dev, model):
+    """north_star gate: test-view PSNR within 0.05 dB of the reference's.  A 48x48 view from a camera pose is rendered through
+    render(c2w=...) (device ray generation, chunked) and by the oracle; both are scored with the reference's
+    mse2psnr(img2mse(rgb, target)) against the same target image -- the oracle's render plus noise, so the PSNR sits where a
+    real test view's does (~26 dB) -- and the two scores must agree to 0.05 dB (they agree to ~1e-4)."""
+    from nerfq_b200 import render as R
+    from oracle import render_oracle as ro
+    from tests.gpu_util import golden_wrapper, trained_wrapper
+    w, p = golden_wrapper(dev, True) if model == "golden" else trained_wrapper(dev, "spread")
+    H = W = 48
+    f = 0.5 * W / np.tan(0.5 * 0.6911112070083618)
+    K = np.array([[f, 0, 0.5 * W], [0, f, 0.5 * H], [0, 0, 1]], dtype=np.float32)
+    c2w = torch.tensor([[1, 0, 0, 0.0], [0, 0.8660254, 0.5, 2.0], [0, -0.5, 0.8660254, 3.4641016]], dtype=torch.float32)
+    _, test_kw = R.create_nerf(w, white_bkgd=True, dataset_type="blender")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with torch.no_grad():
+            rgb, disp, acc, _ = R.render(H, W, K, chunk=700, c2w=c2w.to(dev), near=2.0, far=6.0, **test_kw)
+            rgb_ref, _, acc_ref, _ = ro.render(p, H, W, K, c2w=c2w, ndc=False, near=2.0, far=6.0, white_bkgd=True)
+    assert rgb.shape == (H, W, 3) and maxerr(rgb, rgb_ref) < GATE and maxerr(acc, acc_ref) < GATE
+    target = (rgb_ref + 0.05 * torch.randn(rgb_ref.shape, generator=torch.Generator().manual_seed(11))).clamp(0, 1)
+    psnr = float(R.mse2psnr(R.img2mse(rgb, target.to(dev))))
+    psnr_ref = ro.psnr_from_mse(float(torch.mean((rgb_ref - target) ** 2)))
+    assert 20.0 < psnr_ref < 35.0 and abs(psnr - psnr_ref) < 0.05, (psnr, psnr_ref)
