@@ -653,14 +653,21 @@ def dp_checks(dev, rank, world, timed, rays_d, t_d, step_kw):
     out = {}
     # (a) exposed time: the same captured step with the fused peer-memory finalize (default when the ranks can map each
     # other's memory), with one NCCL all-reduce, and with the collective switched off
-    res = {}
+    steps3 = {}
     for name, kw_dp in (("peer", dict(enabled=True)), ("nccl", dict(enabled=True, peer=False)), ("off", dict(enabled=False))):
         D.enable_data_parallel(**kw_dp)
         if name == "peer":
             out["collective"] = R.DATA_PARALLEL["collective"]
         st = lsa.LSAStep(make(), RAYS_PER_GPU, requantize=None, **step_kw)
         st.capture()
-        res[name] = timed(lambda: st(rays_d, t_d), 20, 5)
+        steps3[name] = st
+    # three rounds, interleaved, best of three per variant: one timed region is +-0.05 ms on these power-capped boxes,
+    # the same order of magnitude as the quantity measured
+    res = {k: float("inf") for k in steps3}
+    for _ in range(3):
+        for name, st in steps3.items():
+            res[name] = min(res[name], timed(lambda: st(rays_d, t_d), 20, 3))
+    for st in steps3.values():
         st.graph = None
     # (b) the NCCL collective alone: one int64[2, 2440] all-reduce
     fix = torch.zeros((2, 2440), dtype=torch.int64, device=dev)
