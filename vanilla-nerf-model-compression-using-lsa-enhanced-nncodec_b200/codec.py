@@ -9,7 +9,7 @@ the float `weight` parameters are set to level*delta so `state_dict()` matches w
 Only uniform reconstruction quantisation (use_dq=False) runs on the GPU; dependent (trellis) quantisation is the
 reference's default and lives in deepCABAC, which is absent here (parity unpinned).
 """
-from typing import Dict
+from typing import Dict, Optional
 
 import torch
 
@@ -17,8 +17,10 @@ from . import ops, packed
 from .model import NeRF
 
 
-def _quantize_nets(nets, qp: int, qp_density: int, nonweight_qp: int):
-    """One launch pair for every weight and bias of `nets`: levels out, parameters overwritten with level*delta."""
+def _quantize_nets(nets, qp: int, qp_density: int, nonweight_qp: int, sources=None):
+    """One launch pair for every weight and bias of `nets`: levels out, parameters overwritten with level*delta.
+    sources: optional {id(parameter tensor): float32 tensor to quantise instead of the parameter's current value} -- the
+    unquantised master copy; the parameters then only receive the reconstruction."""
     tensors, qps, reuse = [], [], []
     for net in nets:
         # a requantisation writes into the level tensors the network already holds (no new allocation: the python attributes
@@ -31,9 +33,10 @@ def _quantize_nets(nets, qp: int, qp_density: int, nonweight_qp: int):
             reuse += [prev[i] if ok else None, None]
     for x in tensors:
         assert x.dtype == torch.float32 and x.is_contiguous()
+    srcs = tensors if sources is None else [sources[x.data_ptr()] for x in tensors]
     outs = []
     for i in range(0, len(tensors), 64):
-        lv, _ = ops.quantize_batch(tensors[i:i + 64], qps[i:i + 64], qp_density, reconstruct_in_place=True, levels_out=reuse[i:i + 64])
+        lv, _ = ops.quantize_batch(srcs[i:i + 64], qps[i:i + 64], qp_density, levels_out=reuse[i:i + 64], reconstruct_into=tensors[i:i + 64])
         outs += lv
     step = ops.stepsize(qp, qp_density)
     res, k = [], 0
@@ -56,9 +59,15 @@ def quantize_net(net: NeRF, qp: int, qp_density: int = 2, nonweight_qp: int = -7
 
 
 @torch.no_grad()
-def quantize_model(wrapper, qp: int, qp_density: int = 2, nonweight_qp: int = -75):
-    """Quantise + reconstruct both networks of a NeRFWrapper in place; returns {net: {tensor: int32 levels}}."""
-    a, b = _quantize_nets([wrapper.model, wrapper.model_fine], qp, qp_density, nonweight_qp)
+def quantize_model(wrapper, qp: int, qp_density: int = 2, nonweight_qp: int = -75, master_state: Optional[dict] = None):
+    """Quantise + reconstruct both networks of a NeRFWrapper in place; returns {net: {tensor: int32 levels}}.
+    master_state: optional state_dict-shaped {name: float32 tensor} of UNQUANTISED values to quantise from (the wrapper's
+    parameters then receive level*delta without being read) -- what a per-step requantisation uses."""
+    sources = None
+    if master_state is not None:
+        sd = wrapper.state_dict()
+        sources = {sd[k].data_ptr(): master_state[k].contiguous() for k in sd if k.endswith(".weight") or k.endswith(".bias")}
+    a, b = _quantize_nets([wrapper.model, wrapper.model_fine], qp, qp_density, nonweight_qp, sources)
     return {"model": a, "model_fine": b}
 
 

@@ -244,13 +244,9 @@ class LSAStep:
 def make_requantizer(wrapper, master_state: dict, qp: int, qp_density: int = 2, nonweight_qp: int = -75):
     """The 'quantise' leg of BASELINE cfg2 as a graph-capturable callable: restore the unquantised float weights and
     biases from `master_state`, quantise + reconstruct them on the GPU (nnc_core/approximator/__init__.py:655-661)."""
-    sd = wrapper.state_dict()
-    keys = [k for k in master_state if k.endswith(".weight") or k.endswith(".bias")]
-    dst = [sd[k] for k in keys]
-    src = [master_state[k] for k in keys]
+    master = {k: v.detach().float().contiguous() for k, v in master_state.items() if k.endswith(".weight") or k.endswith(".bias")}
 
     def requantize():
-        with torch.no_grad():
-            torch._foreach_copy_(dst, src)
-        codec.quantize_model(wrapper, qp, qp_density, nonweight_qp)
+        # quantise FROM the master copy INTO the parameters: no restore-copy of the 4.8 MB of floats per step
+        codec.quantize_model(wrapper, qp, qp_density, nonweight_qp, master_state=master)
     return requantize

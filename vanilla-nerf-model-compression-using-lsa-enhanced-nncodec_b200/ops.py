@@ -84,9 +84,10 @@ def quantize_urq(w: torch.Tensor, qp: int, qp_density: int):
 
 
 def quantize_batch(tensors: Sequence[torch.Tensor], qps: Sequence[int], qp_density: int, reconstruct_in_place: bool = False,
-                   levels_out: Optional[Sequence[torch.Tensor]] = None):
+                   levels_out: Optional[Sequence[torch.Tensor]] = None, reconstruct_into: Optional[Sequence[torch.Tensor]] = None):
     """Quantise many float32 tensors with one launch pair: returns (list of int32 level tensors, qp_used int32[T]).
-    reconstruct_in_place overwrites each input with level*delta (what `rec(approx(x))` yields in the reference)."""
+    reconstruct_in_place overwrites each input with level*delta (what `rec(approx(x))` yields in the reference);
+    reconstruct_into writes level*delta into other tensors of the same shapes instead (the inputs stay untouched)."""
     t = len(tensors)
     assert t == len(qps) and 0 < t <= 64
     dev = tensors[0].device
@@ -98,7 +99,14 @@ def quantize_batch(tensors: Sequence[torch.Tensor], qps: Sequence[int], qp_densi
     vp = _c.c_void_p * t
     w_arr = vp(*[x.data_ptr() for x in tensors])
     l_arr = vp(*[x.data_ptr() for x in lv])
-    r_arr = vp(*[x.data_ptr() for x in tensors]) if reconstruct_in_place else None
+    r_arr = None
+    if reconstruct_into is not None:
+        assert len(reconstruct_into) == t
+        for x, r in zip(tensors, reconstruct_into):
+            assert r.is_cuda and r.dtype == torch.float32 and r.is_contiguous() and r.numel() == x.numel()
+        r_arr = vp(*[r.data_ptr() for r in reconstruct_into])
+    elif reconstruct_in_place:
+        r_arr = vp(*[x.data_ptr() for x in tensors])
     n_arr = (_c.c_longlong * t)(*[x.numel() for x in tensors])
     q_arr = (_c.c_int * t)(*[int(q) for q in qps])
     _lib.check(L().nerfq_quantize_batch(w_arr, l_arr, r_arr, n_arr, q_arr, t, int(qp_density), ws[t:].data_ptr(), ws.data_ptr(), _stream()),
