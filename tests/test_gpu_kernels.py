@@ -298,3 +298,52 @@ def test_mlp_kernels_stay_inside_their_buffers(dev):
     torch.cuda.synchronize()
     assert (d_scale[2436:] == 777.0).all() and torch.isfinite(d_scale[:2436]).all() and float(d_scale[:2436].abs().max()) > 0
     assert (save[save_bytes:] == 0x5A).all() and (raw[n * S * 4:] == 777.0).all()
+
+
+@pytest.mark.parametrize("n,S,Ni", [(37, 33, 21), (13, 64, 128), (5, 17, 5), (9, 200, 56)])
+def test_ray_kernels_stay_inside_their_buffers(dev, n, S, Ni):
+    """Ragged sizes through the C ABI with sentinel-filled guard regions behind every output of the ray-side kernels (depths,
+    compositing forward / backward, sampling + sort with its vector stores): nothing is written outside the documented
+    extents, and every documented element is written."""
+    import ctypes as C
+    ops = _ops()
+    L = ops.L()
+    gen = torch.Generator().manual_seed(n * 1000 + S)
+    rays = synth_rays(n, 17).to(dev)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    G, SENT = 1024, 777.0
+
+    def guarded(count):
+        return torch.full((count + G,), SENT, device=dev)
+
+    def check(buf, count, name):
+        torch.cuda.synchronize()
+        assert (buf[count:] == SENT).all(), f"{name}: wrote past its end"
+        assert not (buf[:count] == SENT).any(), f"{name}: left elements unwritten"
+    t_rand = torch.rand(n, S, generator=gen).to(dev)
+    z = guarded(n * S)
+    assert L.nerfq_coarse_depths(p(rays), p(t_rand), C.c_longlong(n), S, 0, p(z), stream) == 0
+    check(z, n * S, "coarse_depths")
+    z0 = z[:n * S].reshape(n, S).contiguous()
+    raw = torch.randn(n, S, 4, generator=gen).to(dev)
+    rgb, disp, acc, depth, wts = guarded(3 * n), guarded(n), guarded(n), guarded(n), guarded(n * S)
+    assert L.nerfq_composite_fwd(p(raw), p(z0), p(rays), None, 1, C.c_longlong(n), S, p(rgb), p(disp), p(acc), p(depth), p(wts), stream) == 0
+    for buf, cnt, name in ((rgb, 3 * n, "rgb"), (acc, n, "acc"), (depth, n, "depth"), (wts, n * S, "weights")):
+        check(buf, cnt, "composite_fwd " + name)
+    torch.cuda.synchronize()
+    assert (disp[n:] == SENT).all()                      # disp itself may hold NaN (0/0) by the reference's semantics
+    d_rgb = torch.randn(n, 3, generator=gen).to(dev)
+    d_raw = guarded(n * S * 4)
+    assert L.nerfq_composite_bwd(p(raw), p(z0), p(rays), None, 1, p(d_rgb), C.c_longlong(n), S, p(d_raw), stream) == 0
+    check(d_raw, n * S * 4, "composite_bwd")
+    w = wts[:n * S].reshape(n, S).contiguous()
+    for u in (None, torch.rand(n, Ni, generator=gen).to(dev)):
+        z_all, z_std, zs = guarded(n * (S + Ni)), guarded(n), guarded(n * Ni)
+        assert L.nerfq_sample_fine(p(z0), None, p(w), p(u), C.c_longlong(n), S, Ni, p(z_all), p(z_std), p(zs), stream) == 0
+        check(z_all, n * (S + Ni), "sample_fine z_all")
+        check(z_std, n, "sample_fine z_std")
+        check(zs, n * Ni, "sample_fine z_samples")
+        za = z_all[:n * (S + Ni)].reshape(n, S + Ni)
+        assert (za[:, 1:] >= za[:, :-1]).all()
+        assert torch.equal(torch.sort(torch.cat([z0, zs[:n * Ni].reshape(n, Ni)], -1), -1).values, za)
