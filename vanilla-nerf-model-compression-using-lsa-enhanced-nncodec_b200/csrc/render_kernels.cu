@@ -224,13 +224,22 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) composite_bwd_kernel(
     }
 }
 
-// Bitonic sort of 32 * PER values held by a warp, element i = lane * PER + k in register v[k] (blocked layout), ascending.
+// Bitonic sort of 32 * PER keys held by a warp, element i = lane * PER + k in register v[k] (blocked layout), ascending.
 // Strides below PER are compare-exchanges between a thread's own registers; larger strides exchange whole registers with
 // the partner lane by shuffle -- no shared-memory round trips and no barriers (the earlier shared-memory network took
-// 36 passes with a warp barrier each: 164 us per 32768 rays, ncu r02).  A compare-exchange keeps both values of a pair
-// (ties and NaNs are never duplicated or dropped), so the result is the sorted multiset torch.sort would give.
+// 36 passes with a warp barrier each: 164 us per 32768 rays, ncu r02).  The keys are the floats' bits mapped to unsigned
+// integers of the same order (float_key): a compare-exchange is then one integer min / max per element instead of two
+// float compares and selects, a total order exists for every bit pattern (NaN sorts last, like torch.sort), and min / max
+// never duplicate or drop a value -- the result is the sorted multiset.
+__device__ __forceinline__ unsigned float_key(float x) {
+    const unsigned b = __float_as_uint(x);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float key_float(unsigned k) {
+    return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
+}
 template <int PER>
-__device__ __forceinline__ void warp_bitonic_sort(float (&v)[PER], int lane) {
+__device__ __forceinline__ void warp_bitonic_sort(unsigned (&v)[PER], int lane) {
 #pragma unroll
     for (int size = 2; size <= 32 * PER; size <<= 1) {
 #pragma unroll
@@ -242,20 +251,18 @@ __device__ __forceinline__ void warp_bitonic_sort(float (&v)[PER], int lane) {
                 const bool keep_min = lower == asc;
 #pragma unroll
                 for (int k = 0; k < PER; ++k) {
-                    const float mine = v[k];
-                    const float other = __shfl_xor_sync(kFull, mine, m);
-                    const bool take = keep_min ? (other < mine) : (other > mine);
-                    v[k] = take ? other : mine;
+                    const unsigned mine = v[k];
+                    const unsigned other = __shfl_xor_sync(kFull, mine, m);
+                    v[k] = keep_min ? min(mine, other) : max(mine, other);
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < PER; ++k) {
                     if ((k & stride) == 0) {
                         const bool asc = size >= PER ? (((lane * PER) & size) == 0) : ((k & size) == 0);
-                        const float a = v[k], b = v[k | stride];
-                        const bool sw = (a > b) == asc;
-                        v[k] = sw ? b : a;
-                        v[k | stride] = sw ? a : b;
+                        const unsigned a = v[k], b = v[k | stride];
+                        v[k] = asc ? min(a, b) : max(a, b);
+                        v[k | stride] = asc ? max(a, b) : min(a, b);
                     }
                 }
             }
@@ -381,12 +388,15 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_fine_kernel(
     m2 = warp_sum(m2);
     if (lane == 0 && z_std) z_std[ray] = sqrtf(m2 / (float)Ni);
     if (!z_out) return;
-    // sort the P = 32 * PER staged values (coarse depths, samples, +inf padding) in registers
+    // sort the staged values (coarse depths, samples) in registers; slots beyond S + Ni hold the largest key
     __syncwarp();
+    unsigned key[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) key[k] = (lane * PER + k < S + Ni) ? float_key(srt[lane * PER + k]) : 0xffffffffu;
+    warp_bitonic_sort<PER>(key, lane);
     float v[PER];
 #pragma unroll
-    for (int k = 0; k < PER; ++k) v[k] = srt[lane * PER + k];
-    warp_bitonic_sort<PER>(v, lane);
+    for (int k = 0; k < PER; ++k) v[k] = key_float(key[k]);
     float* out = z_out + ray * (S + Ni);
     if (PER % 4 == 0 && (S + Ni) % 4 == 0) {                 // 16-byte stores: a lane's PER values are contiguous
 #pragma unroll
