@@ -352,7 +352,8 @@ __device__ __forceinline__ float column_reduce16_3(float (&p)[16], int lane) {
 }
 
 // The same for 16 per-lane INTEGER columns (fixed-point terms: integer addition is associative, so the result does not depend
-// on the butterfly's order): 15 shuffles instead of 16 warp-wide REDUX, which issue at a fraction of the shuffle rate.
+// on the butterfly's order): 15 shuffles instead of 16 warp-wide REDUX.  Measured the same speed as the REDUX form (0.739 vs
+// 0.737 ms, profiles/r02_ab_wait_hint.log "hint0" vs "base"); kept because the partial sums stay in ordinary registers.
 __device__ __forceinline__ int column_reduce16_i3(int (&p)[16], int lane) {
     int q8[8], q4[4], q2[2];
     {
