@@ -190,3 +190,28 @@ def test_deepcabac_front_end_contract():
     e_w, e_l = np.zeros((0, 7), dtype=np.float32), np.zeros((0, 7), dtype=np.int32)
     assert enc.quantLayer(e_w, e_l, 0, 2, -20, 0.0, 10, 0) == -20
     dec.dequantLayer(e_w, e_l, 2, -20, 0)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the arm the driver divides by): runs on the host cores alone, prints ONE JSON line with the
+    same metric / unit / config.workload as the CUDA arm, `impl: reference`, a cpu_baseline describing the run and an e2e
+    object that repeats the line's value; a non-zero rank under torchrun exits 0 without output."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    sys.path.insert(0, root)
+    import bench
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == "rays/s" and d["higher_is_better"] is True
+    assert d["config"]["workload"] == bench.WORKLOAD and d["config"]["rays_per_step_timed"] in (4096, 1024)
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert abs(d["ms_per_step"] - 1e3 * 4096 / d["value"]) < 1e-6 * d["ms_per_step"] and d["gpu_launches"] == 0
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1"], capture_output=True, text=True,
+                         env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == ""
