@@ -62,8 +62,19 @@ __device__ __forceinline__ void red_global_add_fixed(long long* p, float v) {
 struct H32 { uint4 a, b; };
 __device__ __forceinline__ H32 ldg_nc_32B(const void* p) {
     H32 r;
+#ifndef NERFQ_BWD_LD_POLICY
+#define NERFQ_BWD_LD_POLICY 0
+#endif
+#if NERFQ_BWD_LD_POLICY == 0
     asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w) : "l"(p));
+#elif NERFQ_BWD_LD_POLICY == 1      // read-once data leaves the L2 first (the weight image all SMs stream from it stays)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.L2::256B.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w) : "l"(p));
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w) : "l"(p));
+#endif
     return r;
 }
 
@@ -166,12 +177,17 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
         // registers: a spilled value costs a ~1000-cycle local-memory load per job).  A job's 64 KB slice
         // (mlp3_layout.h, Prog3Bwd::slice_off) is 16 pieces of 4 KB (128 channels x 32 B), one per point chunk, 8 KB
         // apart: 512 lines, one per thread.
-        const uint32_t pf_thread = (uint32_t)e * 8192u + (uint32_t)lane * 128u;
+        const uint32_t pf_thread = (uint32_t)e * 8192u + (NERFQ_BWD_PREFETCH == 3 ? 0u : (uint32_t)lane * 128u);
         // (one request per 128-byte line.  The L2 fills 64 bytes per miss, so this covers half of every slice -- ncu r02 counted
         // exactly 50 % of the demand loads' sectors as L2 misses -- but requesting both halves, NERFQ_BWD_PREFETCH = 2, measured
         // 5 % SLOWER (0.953 vs 0.906 ms) and no prefetch at all 1 % slower: profiles/r02_ab_prefetch_and_saver_waits.log)
         auto prefetch_seq = [&](int g, int v) {      // v: index into [views, job 0 .. 17]
             const uint8_t* line = prm.save + (size_t)g * kSave3GroupBytes + (pf_thread + prm.prog.slice_off[v]);
+            if (NERFQ_BWD_PREFETCH == 3) {
+                // the warp's whole 4 KB piece (all 32 lines, both halves of each) as ONE request to the copy engine
+                if (lane == 0) bulk_prefetch_l2(line, 4096);
+                return;
+            }
             if (NERFQ_BWD_PREFETCH >= 1) prefetch_l2_line(line);
             if (NERFQ_BWD_PREFETCH >= 2) prefetch_l2_line(line + 64);
         };

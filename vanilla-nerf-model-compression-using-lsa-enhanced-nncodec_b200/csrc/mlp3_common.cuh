@@ -102,6 +102,9 @@ __device__ __forceinline__ uint32_t setup3(uint8_t* smem, uint32_t sbase, int wa
 // against the 32 B/clk the MMAs consume, so kLoaders3 warps share the stream: warp `which` copies the chunks with
 // sequence number = which (mod kLoaders3).
 constexpr int kLoaders3 = 2;
+#ifndef NERFQ_WEIGHT_L2_POLICY
+#define NERFQ_WEIGHT_L2_POLICY 0
+#endif
 __device__ __forceinline__ void loader3(uint32_t sbase, const uint8_t* img, int n_chunks, int n_iters, int which) {
     auto bar = [&](int i) { return sbase + kS3Bars + 8u * i; };
     uint32_t seq = 0;
@@ -113,7 +116,11 @@ __device__ __forceinline__ void loader3(uint32_t sbase, const uint8_t* img, int 
             mbar_wait_relaxed(bar(kB3WEmpty) + 8 * slot, par ^ 1);
             if (elect_one()) {
                 mbar_arrive_expect_tx(bar(kB3WFull) + 8 * slot, kChunk3Bytes);
+#if NERFQ_WEIGHT_L2_POLICY == 1
+                bulk_g2s_evict_last(sbase + kS3Ring + slot * kChunk3Bytes, src, kChunk3Bytes, bar(kB3WFull) + 8 * slot);
+#else
                 bulk_g2s(sbase + kS3Ring + slot * kChunk3Bytes, src, kChunk3Bytes, bar(kB3WFull) + 8 * slot);
+#endif
             }
             __syncwarp();
         }

@@ -167,6 +167,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
 }
+// the same copy with an L2 eviction policy: NERFQ_WEIGHT_L2_POLICY = 1 keeps the weight image (read by every SM, every group)
+// in the L2 ahead of the streamed activations
+__device__ __forceinline__ void bulk_g2s_evict_last(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+// ask the copy engine to bring [p, p + bytes) into the L2 (no destination, no completion); bytes a multiple of 16
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  ::"l"(dst_gmem), "r"(src_smem), "r"(bytes) : "memory");
