@@ -85,6 +85,9 @@ int nerfq_set_scale_bias(void* packed, const float* scale, const float* bias, ne
  * save (nullable): nerfq_mlp_save_bytes(n_rays*S) bytes receiving the activations the backward needs.
  * max_ctas: 0 = one CTA per SM.  The result does not depend on max_ctas, on how the rays are split over calls, or on
  * the run: partial sums that meet in arbitrary order are accumulated in fixed point.
+ * Ranges: activations are stored as fp16 and saturate at +-65504 instead of overflowing; the sigma logit before its bias
+ * (the alpha head's sum over 256 channels) is accumulated as a 32-bit integer in units of 2^-18, i.e. it must lie within
+ * +-8192 (partial sums may wrap, the total may not); a volume density that large saturates alpha long before.
  * ---------------------------------------------------------------------------------------------- */
 int nerfq_mlp_forward(const void* packed, const float* rays, const float* z, long long n_rays, int samples_per_ray,
                       float* raw, void* save, int max_ctas, nerfq_stream_t stream);
