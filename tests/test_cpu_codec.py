@@ -197,3 +197,32 @@ def test_unmodified_reference_compress_decompress(dc, tmp_path, use_dq):
             worst = max(worst, float(np.abs(got - v.numpy()).max()))
     # reconstruction error: the quantiser's bound (delta/2 uniform, 2 delta on the trellis) plus the applied scale's effect
     assert worst < (2.0 if use_dq else 0.5) * d_w + 0.15 * float(max(v.abs().max() for v in plain_sd.values()))
+
+
+def test_frozen_stream(dc):
+    """tests/golden/coder_stream.npz (made by tests/golden/make_coder_golden.py with THIS repository's coder: self-pinned, see the
+    script's header): quantising the stored floats reproduces the stored levels (uniform and trellis), encoding them reproduces the
+    stored bytes, and decoding the stored bytes yields the stored levels with exact byte accounting.  A change of the written
+    format fails here."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "coder_stream.npz"))
+    keys, dqs, qps = [str(k) for k in g["layer_keys"]], g["layer_dq"].tolist(), g["layer_qp"].tolist()
+    enc = dc.Encoder()
+    for key, dq, qp in zip(keys, dqs, qps):
+        w = g[key[len("levels_"):key.rindex("_dq")]]
+        lv = np.zeros(w.shape, dtype=np.int32)
+        enc.initCtxModels(10, 0)
+        assert enc.quantLayer(w, lv, dq, 2, qp, 0.0, 10, 0) == qp
+        assert (lv == g[key]).all(), key
+        enc.iae_v(8, qp + 128)
+        enc.encodeLayer(lv, dq, 0)
+    stream = enc.finish().tobytes()
+    assert stream == g["stream"].tobytes()
+    dec = dc.Decoder()
+    dec.setStream(bytearray(g["stream"].tobytes() + b"\xff\x00"))
+    for key, dq, qp in zip(keys, dqs, qps):
+        dec.initCtxModels(10)
+        assert dec.iae_v(8) == qp + 128
+        out = np.zeros(g[key].shape, dtype=np.int32)
+        dec.decodeLayer(out, dq, 0)
+        assert (out == g[key]).all(), key
+    assert dec.finish() == g["stream"].size

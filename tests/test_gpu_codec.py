@@ -63,3 +63,20 @@ def test_block_ndu_gpu_levels_through_the_host_coder():
         dec.dequantLayer(rec, out, 2, qp, 0)
         assert np.abs(rec - t.cpu().numpy()).max() <= 0.5 * ops.stepsize(qp, 2) * (1 + 1e-6)
     assert dec.finish() == len(bs)
+
+
+def test_gpu_levels_match_the_frozen_stream_fixture():
+    """tests/golden/coder_stream.npz: the uniform-quantiser levels stored there (made on the host) come out of the CUDA kernel bit
+    for bit, and the stream's decoded levels dequantise on the GPU to level * delta exactly."""
+    import os
+    from nerfq_b200 import deepcabac as dc, ops
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "coder_stream.npz"))
+    dev = torch.device("cuda:0")
+    for key, dq, qp in zip([str(k) for k in g["layer_keys"]], g["layer_dq"].tolist(), g["layer_qp"].tolist()):
+        w = g[key[len("levels_"):key.rindex("_dq")]]
+        if dq == 0:
+            lv, used = ops.quantize_urq(torch.from_numpy(w).to(dev).contiguous(), qp, 2)
+            assert int(used) == qp and (lv.cpu().numpy() == g[key]).all(), key
+        rec = ops.dequantize(torch.from_numpy(g[key]).to(dev).contiguous(), qp, 2).cpu().numpy()
+        d = np.float32(dc.host_lib().nncabac_stepsize(qp, 2))
+        assert (rec == g[key].astype(np.float32) * d).all(), key
