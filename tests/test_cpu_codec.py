@@ -226,3 +226,45 @@ def test_frozen_stream(dc):
         dec.decodeLayer(out, dq, 0)
         assert (out == g[key]).all(), key
     assert dec.finish() == g["stream"].size
+
+
+def test_decoder_survives_garbage(dc):
+    """Random, truncated and bit-flipped streams: the decoder either returns levels or raises CoderError -- it never reads
+    outside the buffer, loops or crashes -- and whatever it returns re-encodes to a stream that decodes to the same levels."""
+    rng = np.random.default_rng(8)
+
+    def attempt(stream, n, dq, unary=10):
+        dec = dc.Decoder()
+        dec.setStream(bytearray(stream))
+        out = np.zeros(n, dtype=np.int32)
+        try:
+            dec.initCtxModels(unary)
+            dec.decodeLayer(out, dq, 0)
+        except dc.CoderError:
+            return None
+        try:
+            dec.finish()
+        except dc.CoderError:
+            pass                                               # levels came out, the termination pattern did not match
+        return out
+
+    decoded = 0
+    for trial in range(400):
+        size = int(rng.integers(0, 64)) if trial % 2 else 4096
+        out = attempt(bytes(rng.integers(0, 256, size).astype(np.uint8)), int(rng.integers(1, 300)), trial & 1, int(rng.integers(0, 31)))
+        if out is not None and not (trial & 1):
+            decoded += 1
+            _roundtrip(dc, [(out, 0, -20)])
+    assert decoded > 0
+    lv = np.round(rng.standard_normal(3000) * 50).astype(np.int32)
+    enc = dc.Encoder()
+    enc.initCtxModels(10, 0)
+    enc.encodeLayer(lv, 0, 0)
+    good = enc.finish().tobytes()
+    for cut in range(0, len(good), max(1, len(good) // 60)):
+        attempt(good[:cut], 3000, 0)
+    for _ in range(100):
+        b = bytearray(good)
+        b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        attempt(bytes(b), 3000, 0)
+    assert (attempt(good, 3000, 0) == lv).all()
