@@ -165,9 +165,10 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
             s1 += a1.x + a1.y;
             s2 += a2.x + a2.y;
             if (write) {
+                // (row | swz) ^ x == row + (x ^ swz): the row starts on a 128-byte boundary (see the forward kernel)
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
-                    st_shared_v4(row_addr + ((uint32_t)((cc * 2 + k) << 4) ^ swz), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+                    st_shared_v4((row_addr | swz) ^ (uint32_t)((cc * 2 + k) << 4), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
             }
         };
         // chunk cc (0..3) of this thread's 64 points: 32 bytes, 8 KB apart (mlp3_layout.h, save3_offset)

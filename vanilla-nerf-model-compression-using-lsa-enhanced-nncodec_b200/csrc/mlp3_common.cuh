@@ -243,11 +243,33 @@ __device__ __forceinline__ void issuer3(uint32_t sbase, uint32_t tmem_base, int 
 // ---- positional encoding (run_nerf_helpers.py:23-49), split in two halves of 5 levels --------------------
 // levels [l0, l0+5) of gamma(p): out[6*i + c] = sin(2^(l0+i) p_c), out[6*i + 3 + c] = cos(2^(l0+i) p_c).
 // sincosf once per coordinate, then angle doubling (error < 2^4 ulp, far below the fp16 operand rounding).
+// NERFQ_PE_FAST = 1 (default): sin / cos of the base level by an explicit two-constant reduction to [-pi, pi] and the
+// special-function unit (sin.approx / cos.approx: absolute error ~5e-7 there) instead of sincosf (~45 instructions per call,
+// three calls per thread and group, inside the job that hands the encodings to the next group's first layer -- on the
+// dependency chain of the whole CTA: forward 0.700 -> 0.683 ms, forward + save 0.955 -> 0.916 ms,
+// profiles/r02_ab_pe_fast_f32x2.log).  After four angle doublings the error is < 2e-5, a twelfth of the fp16 rounding the
+// encodings get as tensor-core operands (2.4e-4); every parity gate holds unchanged.  Valid for |x| < ~1e4 (the largest
+// argument here is 32 * |p|); beyond that the reduction loses accuracy gracefully (no NaN for finite x).
+#ifndef NERFQ_PE_FAST
+#define NERFQ_PE_FAST 1
+#endif
+__device__ __forceinline__ void sincos_pe(float x, float* s, float* c) {
+#if NERFQ_PE_FAST
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(k, -6.2831854820251465f, x);          // 2 pi = 6.2831854820251465 - 1.7484555e-07
+    r = fmaf(k, 1.7484555e-07f, r);
+    *s = __sinf(r);
+    *c = __cosf(r);
+#else
+    sincosf(x, s, c);
+#endif
+}
+
 __device__ __forceinline__ void encode5(const float p[3], float scale, float* out /* 30 */) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         float s, co;
-        sincosf(p[c] * scale, &s, &co);
+        sincos_pe(p[c] * scale, &s, &co);
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
             if (i > 0) {
@@ -291,7 +313,7 @@ __device__ __forceinline__ void write_dir_enc(uint32_t enc, int row, const float
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         float s, co;
-        sincosf(d[c], &s, &co);
+        sincos_pe(d[c], &s, &co);
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
             if (l > 0) {

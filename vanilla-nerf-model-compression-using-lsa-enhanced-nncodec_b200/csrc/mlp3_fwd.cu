@@ -49,6 +49,9 @@ struct Fwd3Params {
     Prog3Fwd prog;
 };
 
+#ifndef NERFQ_EPI_F32X2
+#define NERFQ_EPI_F32X2 1
+#endif
 constexpr float kAlphaFix = 262144.0f;       // 2^18: fixed-point unit of the alpha-head sum (int32: +-8192 logit units)
 #ifndef NERFQ_SAVE_IN_JOB
 #define NERFQ_SAVE_IN_JOB 2
@@ -206,15 +209,29 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                 const bool relu = f & JB_RELU;
                 const uint32_t row_addr = act + (ch >> 3) * kKGroup3 + pq_j * kNGroup3 + (ch & 7u) * 128u;
                 const uint32_t swz = (ch & 7u) << 4;
+                // the row starts on a 128-byte boundary (tile 1 KB-aligned, all terms multiples of 128): row + (x ^ swz) == (row | swz) ^ x
+                // for the 16-byte slots x = 0..7 << 4 -- one instruction per store address instead of two
+                const uint32_t st_base = row_addr | swz;
                 uint8_t* save_ch = kSave ? save_g + (size_t)jb.slot * kSave3SlotBytes + save3_offset(0, ch) : nullptr;
                 uint32_t va[16], vb[16];
+                // 0: scalar fma everywhere; 1: packed pairs in the kernel without save (measured on one box, profiles/r02_ab_pe_fast_f32x2.log:
+                // forward 0.683 -> 0.666 ms, but forward + save 0.916 -> 0.932 ms -- there the stores' register hazards decide); 2: both
+                constexpr bool kEpiF32x2 = NERFQ_EPI_F32X2 == 2 || (NERFQ_EPI_F32X2 == 1 && !kSave);
+                const uint64_t cx2 = pack_f32x2(c.x, c.x), cy2 = pack_f32x2(c.y, c.y);
                 // (relu_c / alpha_c are compile-time tags: the job's kind is decided ONCE, before its four chunks, instead of by
                 // two branches inside every chunk -- ncu r02 had 15 % of the epilogue's stall samples in branch resolution)
                 auto process = [&](const uint32_t (&v)[16], int cc, auto relu_c, auto alpha_c) {
                     float y[16];
                     uint32_t pk[8];
+                    if (kEpiF32x2) {
+                        // two accumulator values per instruction (fma.rn.f32x2, SASS FFMA2; same IEEE results as the scalar form):
+                        // a job is bound by the length of its instruction stream, not by the FP32 pipe
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) y[i] = fmaf(__uint_as_float(v[i]), c.x, c.y);
+                        for (int i = 0; i < 8; ++i) fma_f32x2(y[2 * i], y[2 * i + 1], v[2 * i], v[2 * i + 1], cx2, cy2);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) y[i] = fmaf(__uint_as_float(v[i]), c.x, c.y);
+                    }
                     if (ab_math) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) pk[i] = v[2 * i] ^ v[2 * i + 1];
@@ -238,7 +255,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                     if (!ab_st) {
 #pragma unroll
                         for (int k = 0; k < 2; ++k)
-                            st_shared_v4(row_addr + ((uint32_t)((cc * 2 + k) << 4) ^ swz), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+                            st_shared_v4(st_base ^ (uint32_t)((cc * 2 + k) << 4), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
                     }
                     // the same 16 values go to the saved-activation slot: the warp's 32 channels are adjacent, 1 KB per store
                     if (kSave && cc < kSaveInJob) st_global_v8(save_ch + save3_offset(pq * 4 + cc, 0), pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
@@ -300,8 +317,8 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                     // thread rewrites these rows, at the next layer) and stored after the hand-over.
 #pragma unroll
                     for (int cc = kSaveInJob; cc < 4; ++cc) {
-                        const uint4 v0 = ld_shared_v4(row_addr + ((uint32_t)((cc * 2) << 4) ^ swz));
-                        const uint4 v1 = ld_shared_v4(row_addr + ((uint32_t)((cc * 2 + 1) << 4) ^ swz));
+                        const uint4 v0 = ld_shared_v4(st_base ^ (uint32_t)((cc * 2) << 4));
+                        const uint4 v1 = ld_shared_v4(st_base ^ (uint32_t)((cc * 2 + 1) << 4));
                         st_global_v8(save_ch + save3_offset(pq * 4 + cc, 0), v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w);
                     }
                 }

@@ -416,6 +416,19 @@ __device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, 
                  ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3) : "memory");
 #endif
 }
+// packed fp32 pairs (sm_100: add / mul / fma .f32x2 on 64-bit registers)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+// {y0, y1} = {a0, a1} * m2 + c2   (a0, a1: raw fp32 bit patterns, e.g. straight from tcgen05.ld)
+__device__ __forceinline__ void fma_f32x2(float& y0, float& y1, uint32_t a0, uint32_t a1, uint64_t m2, uint64_t c2) {
+    uint64_t a, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(m2), "l"(c2));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(y0), "=f"(y1) : "l"(d));
+}
 // {lo, hi} -> packed fp16 pair, round to nearest, saturating at +-65504 instead of producing inf (one F2FP either way);
 // the relu form clamps negative inputs to +0 in the same instruction
 __device__ __forceinline__ uint32_t cvt_pack_f16(float lo, float hi) {
