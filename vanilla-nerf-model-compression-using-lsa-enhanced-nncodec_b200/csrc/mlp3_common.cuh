@@ -306,6 +306,51 @@ __device__ __forceinline__ void write_pe_half(uint32_t enc, int row, int role, c
     write_enc32(enc, row, role * 32, v);
 }
 
+// One 16-column part of the role-0 half (columns 0..31 = [y, z, levels 0..4]): part 0 -> columns 0..15 = [y, z, level 0, level 1,
+// sin(4x), sin(4y)], part 1 -> columns 16..31 = [sin(4z), cos(4x), cos(4y), cos(4z), level 3, level 4].  Same arithmetic, in
+// the same order, as write_pe_half(role 0) -- two threads of a point produce exactly the values one thread would.
+__device__ __forceinline__ void write_pe_lo16(uint32_t enc, int row, int part, const float p[3]) {
+    float s[3], c[3], v[16];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sincos_pe(p[k], &s[k], &c[k]);
+    auto dbl = [&]() {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float s2 = 2.0f * s[k] * c[k];
+            const float c2 = fmaf(-2.0f * s[k], s[k], 1.0f);
+            s[k] = s2; c[k] = c2;
+        }
+    };
+    if (part == 0) {
+        v[0] = p[1]; v[1] = p[2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { v[2 + k] = s[k]; v[5 + k] = c[k]; }
+        dbl();
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { v[8 + k] = s[k]; v[11 + k] = c[k]; }
+        dbl();
+        v[14] = s[0]; v[15] = s[1];
+    } else {
+        dbl();
+        dbl();
+        v[0] = s[2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[1 + k] = c[k];
+        dbl();
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { v[4 + k] = s[k]; v[7 + k] = c[k]; }
+        dbl();
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { v[10 + k] = s[k]; v[13 + k] = c[k]; }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        st_shared_v4(enc + sw128_offset(row, 2 * part + ch), cvt_pack_f16(v[8 * ch + 0], v[8 * ch + 1]),
+                     cvt_pack_f16(v[8 * ch + 2], v[8 * ch + 3]), cvt_pack_f16(v[8 * ch + 4], v[8 * ch + 5]),
+                     cvt_pack_f16(v[8 * ch + 6], v[8 * ch + 7]));
+    }
+}
+
 // gamma(d): 27 values (d, then 4 levels) + 5 zeros into columns 0..31
 __device__ __forceinline__ void write_dir_enc(uint32_t enc, int row, const float d[3]) {
     float v[32];

@@ -49,6 +49,9 @@ struct Fwd3Params {
     Prog3Fwd prog;
 };
 
+#ifndef NERFQ_PE_SPLIT
+#define NERFQ_PE_SPLIT 1
+#endif
 #ifndef NERFQ_EPI_F32X2
 #define NERFQ_EPI_F32X2 1
 #endif
@@ -161,6 +164,18 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                 const uint32_t ch = 128u * hi + 32u * q_j + (tid_j & 31u);   // this thread's channel within the layer
                 const float2 c = c_next;
                 const float wa = wa_next;
+#if NERFQ_PE_SPLIT
+                // Encoding work taken OFF the dependency chain.  A warp that gets here has finished job (5, hi): every MMA of L5, the
+                // last reader of this half's gamma(x), has completed, and the accumulator this job waits for cannot be ready before
+                // the issuer has seen that job's hand-over and run two more weight chunks -- a guaranteed gap of > 1000 cycles in
+                // which the even warps write gamma(d) into columns 0..31 and the odd warps the NEXT group's gamma(x) columns 32..63
+                // (the views layer multiplies those columns by zero weights: any finite value may stand there).
+                if ((f & JB_DIR_BEFORE) && !ab_pe) {
+                    const int row = (int)((((tid_j >> 5) - (uint32_t)kEpiWarp0) >> 1) * 32u + (tid_j & 31u));
+                    if (role == 0) write_dir_enc(enc, row, vd);
+                    else if (g + stride < prm.n_groups) write_pe_half(enc, row, 1, p);
+                }
+#endif
                 unsigned long long t0 = 0;
                 if (tracing) t0 = clock64();
                 if (f & JB_ACC_HI) { mbar_wait_acc(bar(kB3AccReady + 2 * team + 1), ph_acc1); ph_acc1 ^= 1; }
@@ -201,9 +216,11 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                     continue;
                 }
 
+#if !NERFQ_PE_SPLIT
                 if (f & JB_DIR_BEFORE) {        // gamma(x) is dead once L5 has been accumulated
                     if (role == 0 && !ab_pe) write_dir_enc(enc, (int)((((tid_j >> 5) - (uint32_t)kEpiWarp0) >> 1) * 32u + (tid_j & 31u)), vd);
                 }
+#endif
                 // ---- 4 chunks of 16 points: TMEM -> y = acc*es + b -> (ReLU) -> fp16 -> operand tile ----
                 // The load of chunk i+1 is in flight while chunk i is converted and stored.
                 const bool relu = f & JB_RELU;
@@ -305,7 +322,12 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                 if (tracing) { const unsigned long long dt = clock64() - t0; t_math += dt; if (j == j_sel) t_sel_math += dt; }
                 if (f & JB_PE_AFTER) {          // the direction stage of this group has been accumulated
                     if (g + stride < prm.n_groups) {
+#if NERFQ_PE_SPLIT
+                        // columns 0..31 held gamma(d) until the views layer was accumulated: the two warps of a point write 16 of them each
+                        if (!ab_pe) write_pe_lo16(enc, (int)((((tid_j >> 5) - (uint32_t)kEpiWarp0) >> 1) * 32u + (tid_j & 31u)), role, p);
+#else
                         if (!ab_pe) write_pe_half(enc, (int)((((tid_j >> 5) - (uint32_t)kEpiWarp0) >> 1) * 32u + (tid_j & 31u)), role, p);
+#endif
 #pragma unroll
                         for (int k = 0; k < 3; ++k) vd[k] = vd_next[k];
                     }
