@@ -49,6 +49,9 @@ struct Fwd3Params {
     Prog3Fwd prog;
 };
 
+#ifndef NERFQ_PREWAIT_SETUP
+#define NERFQ_PREWAIT_SETUP 1
+#endif
 #ifndef NERFQ_PE_SPLIT
 #define NERFQ_PE_SPLIT 1
 #endif
@@ -176,14 +179,28 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                     else if (g + stride < prm.n_groups) write_pe_half(enc, row, 1, p);
                 }
 #endif
+#if NERFQ_PREWAIT_SETUP
+                // everything that does not depend on the accumulator is issued BEFORE the wait for it: the next job's constants, the
+                // operand row and saved-activation addresses (a "low" job finds a gap here; after the wait these would sit on the chain)
+                const uint32_t ta = tmem_lane + ((f & JB_ACC_HI) ? 128u : 0u);
+                load_consts(j + 1 < kFwd3Jobs ? j + 1 : 0, c_next, wa_next);    // in flight during this job
+                const uint32_t row_addr = act + (ch >> 3) * kKGroup3 + pq_j * kNGroup3 + (ch & 7u) * 128u;
+                const uint32_t swz = (ch & 7u) << 4;
+                // the row starts on a 128-byte boundary (tile 1 KB-aligned, all terms multiples of 128): row + (x ^ swz) == (row | swz) ^ x
+                // for the 16-byte slots x = 0..7 << 4 -- one instruction per store address instead of two
+                const uint32_t st_base = row_addr | swz;
+                uint8_t* save_ch = kSave ? save_g + (size_t)jb.slot * kSave3SlotBytes + save3_offset(0, ch) : nullptr;
+#endif
                 unsigned long long t0 = 0;
                 if (tracing) t0 = clock64();
                 if (f & JB_ACC_HI) { mbar_wait_acc(bar(kB3AccReady + 2 * team + 1), ph_acc1); ph_acc1 ^= 1; }
                 else { mbar_wait_acc(bar(kB3AccReady + 2 * team), ph_acc0); ph_acc0 ^= 1; }
                 tc_fence_after_sync();
                 if (tracing) { const unsigned long long t1 = clock64(); t_acc += t1 - t0; t0 = t1; }
+#if !NERFQ_PREWAIT_SETUP
                 const uint32_t ta = tmem_lane + ((f & JB_ACC_HI) ? 128u : 0u);
                 load_consts(j + 1 < kFwd3Jobs ? j + 1 : 0, c_next, wa_next);    // in flight during this job
+#endif
 
                 if (f & JB_FINAL) {
                     // rgb head: lanes 0..2 of the accumulator hold the three logit rows; sigma comes from the alpha
@@ -224,12 +241,12 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_forward_kernel(const __grid
                 // ---- 4 chunks of 16 points: TMEM -> y = acc*es + b -> (ReLU) -> fp16 -> operand tile ----
                 // The load of chunk i+1 is in flight while chunk i is converted and stored.
                 const bool relu = f & JB_RELU;
+#if !NERFQ_PREWAIT_SETUP
                 const uint32_t row_addr = act + (ch >> 3) * kKGroup3 + pq_j * kNGroup3 + (ch & 7u) * 128u;
                 const uint32_t swz = (ch & 7u) << 4;
-                // the row starts on a 128-byte boundary (tile 1 KB-aligned, all terms multiples of 128): row + (x ^ swz) == (row | swz) ^ x
-                // for the 16-byte slots x = 0..7 << 4 -- one instruction per store address instead of two
                 const uint32_t st_base = row_addr | swz;
                 uint8_t* save_ch = kSave ? save_g + (size_t)jb.slot * kSave3SlotBytes + save3_offset(0, ch) : nullptr;
+#endif
                 uint32_t va[16], vb[16];
                 // 0: scalar fma everywhere; 1: packed pairs in the kernel without save (measured on one box, profiles/r02_ab_pe_fast_f32x2.log:
                 // forward 0.683 -> 0.666 ms, but forward + save 0.916 -> 0.932 ms -- there the stores' register hazards decide); 2: both
