@@ -324,13 +324,14 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 const Job3 jn = prm.prog.job[j + 1 < kBwd3Jobs ? j + 1 : j];
                 const uint8_t* hrow_next = saved_row(gj, jn.slot, ((jn.flags & JB_HI_HALF) ? 128u : 0u) + cl);
                 if (j + 1 + NERFQ_BWD_PF_DIST <= kBwd3Jobs) prefetch_seq(gj, j + 1 + NERFQ_BWD_PF_DIST);      // NERFQ_BWD_PF_DIST jobs ahead, into L2 (one line per thread)
+                c_next = __ldg(&g_sb[prm.prog.job[j + 1 < kBwd3Jobs ? j + 1 : 0].ch + cl]);        // in flight during this job; issued before
+                                                                                                     // the wait like everything that does not need the accumulator
                 unsigned long long tj0 = 0;
                 if (tracing) tj0 = clock64();
                 if (hi) { mbar_wait_acc(bar(kB3AccReady + 2 * team + 1), ph_acc1); ph_acc1 ^= 1; }
                 else { mbar_wait_acc(bar(kB3AccReady + 2 * team), ph_acc0); ph_acc0 ^= 1; }
                 tc_fence_after_sync();
                 if (tracing) { const unsigned long long t = clock64(); t_acc += t - tj0; tj0 = t; }
-                c_next = __ldg(&g_sb[prm.prog.job[j + 1 < kBwd3Jobs ? j + 1 : 0].ch + cl]);        // in flight during this job
                 const uint32_t ta = tmem_lane + (hi ? 128u : 0u);
                 const bool relu = f & JB_RELU, write = !(f & JB_NO_WRITE);
                 float s1 = 0.0f, s2 = 0.0f;
