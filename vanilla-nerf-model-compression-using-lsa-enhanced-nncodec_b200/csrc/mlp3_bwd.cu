@@ -45,6 +45,9 @@ static_assert(kS3BwdMax + 32 <= kS3Misc, "backward scratch must fit the encoding
 #ifndef NERFQ_BWD_PREFETCH
 #define NERFQ_BWD_PREFETCH 1
 #endif
+#ifndef NERFQ_BWD_HH
+#define NERFQ_BWD_HH 2            // register slots of saved activations in flight per thread: 2 (two chunks ahead) or 4 (a whole job ahead)
+#endif
 #ifndef NERFQ_BWD_PF_DIST
 #define NERFQ_BWD_PF_DIST 2       // how many jobs ahead a job's slice of saved activations is requested into L2
 #endif
@@ -197,6 +200,16 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
             publish(kB3ActHi + team);       // D_hi is free at kernel start
             c_next = __ldg(&g_sb[prm.prog.job[0].ch + cl]);
         }
+#if NERFQ_BWD_HH == 5
+        // a whole job ahead, across groups: the last job of a group requests the first job of the CTA's next group
+        H32 hh[4];
+        if (n_iters > 0) {
+            const Job3 j0 = prm.prog.job[0];
+            const uint8_t* hrow0 = saved_row(first, j0.slot, ((j0.flags & JB_HI_HALF) ? 128u : 0u) + cl);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) hh[cc] = ldg_nc_32B(hrow0 + pair_off(cc, 0));
+        }
+#endif
         int it = 0;
         for (int g = first; g < prm.n_groups; g += stride, ++it) {
             // ================= prologue: head gradients, group scale, views-layer gradient =================
@@ -270,13 +283,15 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
 
             // ---- views-layer job: d hv[k][n] = sum_c g_c[n] * w_rgb[c][k], channels 0..127 ----
             if (tracing) { const unsigned long long t = clock64(); t_pro += t - tp0; tp0 = t; }
-            H32 hh[2];             // saved activations of the dgrad chain's current job, chunks 0 and 1 (see the job loop)
+#if NERFQ_BWD_HH != 5
+            H32 hh[NERFQ_BWD_HH];  // saved activations of the dgrad chain's current job, chunks 0 and 1 (see the job loop)
             {
                 const Job3 j0 = prm.prog.job[0];
                 const uint8_t* hrow0 = saved_row(g, j0.slot, ((j0.flags & JB_HI_HALF) ? 128u : 0u) + cl);
                 hh[0] = ldg_nc_32B(hrow0 + pair_off(0, 0));
                 hh[1] = ldg_nc_32B(hrow0 + pair_off(1, 0));
             }
+#endif
             {
                 const uint32_t chh = cl;                                   // views hidden channel
                 const float2 c = __ldg(&g_sb[kChViews + chh]);
@@ -306,6 +321,14 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
 
             // ================= dgrad chain =================
             if (tracing) t_views += clock64() - tp0;
+#if NERFQ_BWD_HH == 4
+            {
+                const Job3 j0 = prm.prog.job[0];
+                const uint8_t* hrow0 = saved_row(g, j0.slot, ((j0.flags & JB_HI_HALF) ? 128u : 0u) + cl);
+                hh[2] = ldg_nc_32B(hrow0 + pair_off(2, 0));
+                hh[3] = ldg_nc_32B(hrow0 + pair_off(3, 0));
+            }
+#endif
 #pragma unroll 1
             for (int j = 0; j < kBwd3Jobs; ++j) {
                 const Job3 jb = prm.prog.job[j];
@@ -321,8 +344,14 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 // was still running -- the accumulator of a "hi" job is ready long before its job starts, so loads issued at
                 // the job's start had their whole HBM latency exposed (ncu r02: 12 % of all warp samples on their first use).
                 // Each consumed slot is refilled with the chunk two ahead; chunks 2 and 3 free the slots for the next job.
+#if NERFQ_BWD_HH == 5
+                const Job3 jn = prm.prog.job[j + 1 < kBwd3Jobs ? j + 1 : 0];
+                const int gn = j + 1 < kBwd3Jobs ? gj : (gj + stride < prm.n_groups ? gj + stride : gj);
+                const uint8_t* hrow_next = saved_row(gn, jn.slot, ((jn.flags & JB_HI_HALF) ? 128u : 0u) + cl);
+#else
                 const Job3 jn = prm.prog.job[j + 1 < kBwd3Jobs ? j + 1 : j];
                 const uint8_t* hrow_next = saved_row(gj, jn.slot, ((jn.flags & JB_HI_HALF) ? 128u : 0u) + cl);
+#endif
                 if (j + 1 + NERFQ_BWD_PF_DIST <= kBwd3Jobs) prefetch_seq(gj, j + 1 + NERFQ_BWD_PF_DIST);      // NERFQ_BWD_PF_DIST jobs ahead, into L2 (one line per thread)
                 c_next = __ldg(&g_sb[prm.prog.job[j + 1 < kBwd3Jobs ? j + 1 : 0].ch + cl]);        // in flight during this job; issued before
                                                                                                      // the wait like everything that does not need the accumulator
@@ -366,9 +395,17 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                     for (int i = 0; i < 8; ++i) dpk[i] = cvt_pack_f16(__uint_as_float(va[2 * i]), __uint_as_float(va[2 * i + 1]));
                     if (cc < 3) tmem_ld16(ta + 16 * (cc + 1), va);
                     if (cc == 0 && (f & JB_WAIT_SF)) { mbar_wait(bar(kB3StageFree + 2 * team + (q >> 1)), ph_sf); ph_sf ^= 1; }
+#if NERFQ_BWD_HH == 5
+                    const H32 hp = hh[cc];
+                    hh[cc] = ldg_nc_32B(hrow_next + pair_off(cc, swz));          // unconditional: the row always exists
+#elif NERFQ_BWD_HH == 4
+                    const H32 hp = hh[cc];           // a whole job ahead: slot cc is refilled with the next job's chunk cc
+                    if (j + 1 < kBwd3Jobs) hh[cc] = ldg_nc_32B(hrow_next + pair_off(cc, swz));
+#else
                     const H32 hp = hh[cc & 1];
                     if (cc < 2) hh[cc & 1] = ldg_nc_32B(hrow + pair_off(cc + 2, swz));       // refill with chunk cc + 2
                     else if (j + 1 < kBwd3Jobs) hh[cc & 1] = ldg_nc_32B(hrow_next + pair_off(cc - 2, swz));      // next job's chunk cc - 2
+#endif
                     chunk16(dpk, hp.a, hp.b, relu, write, row_addr, swz, cc, s1, s2);
                 }
                 if (write || hi) publish((hi ? kB3ActHi : kB3ActLo) + team);
