@@ -41,7 +41,7 @@ METRIC = "rays/sec render_rays (64+128 samples/ray); LSA steps/sec"
 WORKLOAD = ("cfg2: LSA fine-tuning step at qp=-20 (quantise -> LSA-scaled dequant -> render 4096 rays/GPU, 64+128 samples -> "
             "backward into LSA scales -> Adam), random-init vanilla NeRF, synthetic rays")
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 4096 rays x 192 samples (profiles/)
-NCU_DRAM_BYTES = {"mlp_bwd_fine": 3869400000 + 3700000, "mlp_fwd_fine": 4700000 + 3780200000}      # profiles/r02_ncu_mlp_kernels_summary.txt
+NCU_DRAM_BYTES = {"mlp_bwd_fine": 3871700000 + 8700000, "mlp_fwd_fine": 4700000 + 3782400000}      # profiles/r02_ncu_mlp_kernels_summary.txt (capture at HEAD)
 
 
 def synth_batch(n, seed, device="cpu"):
