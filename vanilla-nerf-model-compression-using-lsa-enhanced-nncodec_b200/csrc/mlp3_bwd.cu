@@ -48,6 +48,17 @@ static_assert(kS3BwdMax + 32 <= kS3Misc, "backward scratch must fit the encoding
 #ifndef NERFQ_BWD_HH
 #define NERFQ_BWD_HH 2            // register slots of saved activations in flight per thread: 2 (two chunks ahead) or 4 (a whole job ahead)
 #endif
+// register budgets of this kernel's control / epilogue warps (4*32*ctrl + 16*32*epi must not exceed the 61,440 registers of
+// the launch allocation: 64 / 104 or 32 / 112)
+#ifndef NERFQ_BWD_REGS_CTRL
+#define NERFQ_BWD_REGS_CTRL NERFQ_REGS_CTRL3
+#endif
+#ifndef NERFQ_BWD_REGS_EPI
+#define NERFQ_BWD_REGS_EPI NERFQ_REGS_EPI3
+#endif
+#ifndef NERFQ_BWD_PIN
+#define NERFQ_BWD_PIN 0
+#endif
 #ifndef NERFQ_BWD_PF_DIST
 #define NERFQ_BWD_PF_DIST 2       // how many jobs ahead a job's slice of saved activations is requested into L2
 #endif
@@ -102,7 +113,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
 
     if (warp >= kCtrlWarp0 && warp < kCtrlWarp0 + kCtrlWarps3) {
         const int cw = warp - kCtrlWarp0;
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 " NERFQ_REGS_CTRL3 ";");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " NERFQ_BWD_REGS_CTRL ";");
         if (cw == 0 || cw == 2) {
             loader3(sbase, prm.packed + kOffBwd3Image, kBwd3Chunks, n_iters, cw >> 1);
         } else {
@@ -110,7 +121,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
         }
     } else {
         // ================= epilogue warps =================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 " NERFQ_REGS_EPI3 ";");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " NERFQ_BWD_REGS_EPI ";");
         // the role dispatch above uses the shuffled (uniform-register) warp index; the per-thread geometry below is derived
         // from threadIdx so that the compiler rematerialises it from the special register rather than spilling it
         const int tw = (int)(threadIdx.x >> 5);
@@ -361,7 +372,13 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                 else { mbar_wait_acc(bar(kB3AccReady + 2 * team), ph_acc0); ph_acc0 ^= 1; }
                 tc_fence_after_sync();
                 if (tracing) { const unsigned long long t = clock64(); t_acc += t - tj0; tj0 = t; }
-                const uint32_t ta = tmem_lane + (hi ? 128u : 0u);
+#if NERFQ_BWD_PIN
+                // keep the job's two addresses in registers: without this the compiler re-derives them from %tid in every chunk
+                uint32_t ta = tmem_lane + (hi ? 128u : 0u), rs = row_addr | swz;
+                asm volatile("" : "+r"(ta), "+r"(rs));
+#else
+                const uint32_t ta = tmem_lane + (hi ? 128u : 0u), rs = row_addr;
+#endif
                 const bool relu = f & JB_RELU, write = !(f & JB_NO_WRITE);
                 float s1 = 0.0f, s2 = 0.0f;
                 uint32_t va[16];
@@ -406,7 +423,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
                     if (cc < 2) hh[cc & 1] = ldg_nc_32B(hrow + pair_off(cc + 2, swz));       // refill with chunk cc + 2
                     else if (j + 1 < kBwd3Jobs) hh[cc & 1] = ldg_nc_32B(hrow_next + pair_off(cc - 2, swz));      // next job's chunk cc - 2
 #endif
-                    chunk16(dpk, hp.a, hp.b, relu, write, row_addr, swz, cc, s1, s2);
+                    chunk16(dpk, hp.a, hp.b, relu, write, rs, swz, cc, s1, s2);
                 }
                 if (write || hi) publish((hi ? kB3ActHi : kB3ActLo) + team);
                 red_global_add_fixed(prm.grad_tmp + jb.ch + cl, (s1 - c.y * s2) * ld_shared_f32(rinv_a));     // after the hand-over

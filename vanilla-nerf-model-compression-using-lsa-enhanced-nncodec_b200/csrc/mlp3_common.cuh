@@ -26,8 +26,12 @@ constexpr int kCtrlWarps3 = 4;
 #endif
 constexpr int kCtrlWarp0 = NERFQ_CTRL_LAST ? 16 : 0;      // first control warp (a multiple of 4: one warp group for setmaxnreg)
 constexpr int kEpiWarp0 = NERFQ_CTRL_LAST ? 0 : 4;        // first epilogue warp
+#ifndef NERFQ_REGS_CTRL3
 #define NERFQ_REGS_CTRL3 "64"
+#endif
+#ifndef NERFQ_REGS_EPI3
 #define NERFQ_REGS_EPI3 "104"
+#endif
 constexpr int kEpiWarps3 = 16;
 constexpr int kThreads3 = 32 * (kCtrlWarps3 + kEpiWarps3);
 constexpr int kSlots3 = 4;
