@@ -46,7 +46,9 @@ static_assert(kS3BwdMax + 32 <= kS3Misc, "backward scratch must fit the encoding
 #define NERFQ_BWD_PREFETCH 1
 #endif
 #ifndef NERFQ_BWD_HH
-#define NERFQ_BWD_HH 2            // register slots of saved activations in flight per thread: 2 (two chunks ahead) or 4 (a whole job ahead)
+// saved activations in flight per thread: 2 = two register slots, a chunk is requested two chunks ahead (default);
+// 5 = four slots, a whole job ahead, also across the CTA's groups (measured equal: profiles/r02_ab_bwd_pinned_addresses_and_register_split.log)
+#define NERFQ_BWD_HH 2
 #endif
 // register budgets of this kernel's control / epilogue warps (4*32*ctrl + 16*32*epi must not exceed the 61,440 registers of
 // the launch allocation: 64 / 104 or 32 / 112)
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
             // ---- views-layer job: d hv[k][n] = sum_c g_c[n] * w_rgb[c][k], channels 0..127 ----
             if (tracing) { const unsigned long long t = clock64(); t_pro += t - tp0; tp0 = t; }
 #if NERFQ_BWD_HH != 5
-            H32 hh[NERFQ_BWD_HH];  // saved activations of the dgrad chain's current job, chunks 0 and 1 (see the job loop)
+            H32 hh[2];             // saved activations of the dgrad chain's current job, chunks 0 and 1 (see the job loop)
             {
                 const Job3 j0 = prm.prog.job[0];
                 const uint8_t* hrow0 = saved_row(g, j0.slot, ((j0.flags & JB_HI_HALF) ? 128u : 0u) + cl);
@@ -332,14 +334,6 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
 
             // ================= dgrad chain =================
             if (tracing) t_views += clock64() - tp0;
-#if NERFQ_BWD_HH == 4
-            {
-                const Job3 j0 = prm.prog.job[0];
-                const uint8_t* hrow0 = saved_row(g, j0.slot, ((j0.flags & JB_HI_HALF) ? 128u : 0u) + cl);
-                hh[2] = ldg_nc_32B(hrow0 + pair_off(2, 0));
-                hh[3] = ldg_nc_32B(hrow0 + pair_off(3, 0));
-            }
-#endif
 #pragma unroll 1
             for (int j = 0; j < kBwd3Jobs; ++j) {
                 const Job3 jb = prm.prog.job[j];
@@ -415,9 +409,6 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp3_backward_kernel(const __gri
 #if NERFQ_BWD_HH == 5
                     const H32 hp = hh[cc];
                     hh[cc] = ldg_nc_32B(hrow_next + pair_off(cc, swz));          // unconditional: the row always exists
-#elif NERFQ_BWD_HH == 4
-                    const H32 hp = hh[cc];           // a whole job ahead: slot cc is refilled with the next job's chunk cc
-                    if (j + 1 < kBwd3Jobs) hh[cc] = ldg_nc_32B(hrow_next + pair_off(cc, swz));
 #else
                     const H32 hp = hh[cc & 1];
                     if (cc < 2) hh[cc & 1] = ldg_nc_32B(hrow + pair_off(cc + 2, swz));       // refill with chunk cc + 2
